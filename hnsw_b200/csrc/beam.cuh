@@ -1,0 +1,412 @@
+// beam.cuh — the traversal core shared by search and construction.
+//
+// Restates, for a group of W warps working on ONE query:
+//   * greedy_update_nearest          -> Beam::descend
+//   * search_from_candidates / search_neighbors_to_add     -> Beam::run
+//     (App. A.6 / A.9; both reduce to "keep the ef best vertices seen, expand the
+//      closest unexpanded one, stop when none is left" — see DESIGN.md §3)
+// with the CPU structures replaced by:
+//   MinimaxHeap + result heap -> one sorted ef-list of 64-bit (dist,id) keys in shared
+//                                memory with an "expanded" bit, merged per hop by rank;
+//   VisitedTable              -> shared-memory open-addressing hash (atomicCAS, linear
+//                                probing). When it fills it is cleared and re-seeded with the
+//                                current list: vertices outside the list can then be re-scored,
+//                                but they were rejected against a threshold that only tightens,
+//                                so results are unchanged (only ndis grows);
+//   fvec_L2sqr / inner product-> TEAM lanes per vector, 128-bit gathers, R vectors in flight
+//                                per team, fixed fmaf order + xor-butterfly (bit-reproducible;
+//                                the oracle's team mode emulates it exactly).
+#pragma once
+#include "common.cuh"
+
+namespace bh {
+
+struct BeamStats {
+    int ndis0 = 0, nhops0 = 0, ndis_up = 0, nhops_up = 0;
+};
+
+// Per-group shared memory carve-up. Host and device must agree: see group_smem_bytes().
+struct GroupSmem {
+    uint64_t* mbar;
+    float4* qbuf;
+    unsigned long long* list[2];
+    int32_t* cand_id;
+    unsigned long long* cand_key;
+    unsigned long long* acc_key;
+    int32_t* ctrl;  // [0]=n_new / stop, [1]=lsize, [2]=cur, [3]=work index
+    uint32_t* hash;
+};
+
+__host__ __device__ inline size_t round16(size_t x) { return (x + 15) & ~size_t(15); }
+
+__host__ __device__ inline size_t group_smem_bytes(int d, int ef, int hash_slots) {
+    return 16 + round16((size_t)d * 4) + 2 * round16((size_t)ef * 8) + round16(kMaxDeg * 4) +
+           2 * round16(kMaxDeg * 8) + 32 + (size_t)hash_slots * 4;
+}
+
+__device__ inline GroupSmem carve_group_smem(unsigned char* p, int d, int ef, int hash_slots) {
+    GroupSmem s;
+    s.mbar = reinterpret_cast<uint64_t*>(p);
+    p += 16;
+    s.qbuf = reinterpret_cast<float4*>(p);
+    p += round16((size_t)d * 4);
+    s.list[0] = reinterpret_cast<unsigned long long*>(p);
+    p += round16((size_t)ef * 8);
+    s.list[1] = reinterpret_cast<unsigned long long*>(p);
+    p += round16((size_t)ef * 8);
+    s.cand_id = reinterpret_cast<int32_t*>(p);
+    p += round16(kMaxDeg * 4);
+    s.cand_key = reinterpret_cast<unsigned long long*>(p);
+    p += round16(kMaxDeg * 8);
+    s.acc_key = reinterpret_cast<unsigned long long*>(p);
+    p += round16(kMaxDeg * 8);
+    s.ctrl = reinterpret_cast<int32_t*>(p);
+    p += 32;
+    s.hash = reinterpret_cast<uint32_t*>(p);
+    return s;
+}
+
+template <int TEAM, int CPL, int W, int R>
+struct Beam {
+    static constexpr int TPW = 32 / TEAM;  // teams per warp
+    static constexpr int NT = TPW * W;     // teams per query group
+
+    const GraphView& g;
+    const GroupSmem& s;
+    const int wig;   // warp index within the group (0 = leader)
+    const int lane;
+    const int bar_id;
+    float4 q[CPL];   // this lane's slice of the query
+
+    __device__ Beam(const GraphView& g_, const GroupSmem& s_, int wig_, int lane_, int bar_id_)
+        : g(g_), s(s_), wig(wig_), lane(lane_), bar_id(bar_id_) {}
+
+    __device__ __forceinline__ void group_sync() const {
+        if (W == 1)
+            __syncwarp();
+        else
+            bar_sync(bar_id, 32 * W);
+    }
+
+    __device__ __forceinline__ void load_query_from_smem() {
+        const int lit = lane % TEAM;
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+            const int chunk = c * TEAM + lit;
+            q[c] = chunk < g.nchunk ? s.qbuf[chunk] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+
+    // Distances from the query to cand_id[0..n): result keys into cand_key[0..n).
+    // Team t scores rows t, t+NT, …; R rows' worth of 128-bit gathers are issued before
+    // the first is consumed.
+    __device__ __forceinline__ void compute_dists(int n) const {
+        const int lit = lane % TEAM;
+        const int team = wig * TPW + lane / TEAM;
+        const float4* __restrict__ base = reinterpret_cast<const float4*>(g.vecs);
+        for (int r0 = 0; r0 < n; r0 += NT * R) {
+            float4 x[R][CPL];
+            int id[R];
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                const int r = r0 + k * NT + team;
+                id[k] = r < n ? s.cand_id[r] : -1;
+            }
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                const float4* row = base + (size_t)(id[k] < 0 ? 0 : id[k]) * g.nchunk;
+#pragma unroll
+                for (int c = 0; c < CPL; c++) {
+                    const int chunk = c * TEAM + lit;
+                    if (id[k] >= 0 && chunk < g.nchunk)
+                        x[k][c] = ldg_stream(row + chunk);
+                    else
+                        x[k][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                float acc = 0.f;
+                if (g.is_l2) {
+#pragma unroll
+                    for (int c = 0; c < CPL; c++) {
+                        float t;
+                        t = q[c].x - x[k][c].x; acc = fmaf(t, t, acc);
+                        t = q[c].y - x[k][c].y; acc = fmaf(t, t, acc);
+                        t = q[c].z - x[k][c].z; acc = fmaf(t, t, acc);
+                        t = q[c].w - x[k][c].w; acc = fmaf(t, t, acc);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CPL; c++) {
+                        acc = fmaf(q[c].x, x[k][c].x, acc);
+                        acc = fmaf(q[c].y, x[k][c].y, acc);
+                        acc = fmaf(q[c].z, x[k][c].z, acc);
+                        acc = fmaf(q[c].w, x[k][c].w, acc);
+                    }
+                }
+#pragma unroll
+                for (int off = TEAM / 2; off >= 1; off >>= 1)
+                    acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
+                if (!g.is_l2) acc = -acc;
+                if (lit == 0 && id[k] >= 0) s.cand_key[r0 + k * NT + team] = pack_key(acc, (uint32_t)id[k]);
+            }
+        }
+    }
+
+    __device__ __forceinline__ const int32_t* row_ptr(int v, int level, int& deg) const {
+        if (level == 0) {
+            deg = g.deg0;
+            return g.nbr0 + (size_t)v * g.deg0;
+        }
+        deg = g.degU;
+        const int b = __ldg(g.upper_base + v);
+        return g.upper_nbr + ((size_t)b + (level - 1)) * g.degU;
+    }
+
+    // Leader warp: load a row, cut it at the first -1 (faiss: `if (v < 0) break`).
+    // ids[i] holds row[lane + 32 i] or -1.
+    __device__ __forceinline__ void load_row(int v, int level, int (&ids)[kMaxIdsPerLane]) const {
+        int deg;
+        const int32_t* row = row_ptr(v, level, deg);
+        int first_neg = kMaxDeg;
+#pragma unroll
+        for (int i = 0; i < kMaxIdsPerLane; i++) {
+            const int idx = lane + 32 * i;
+            ids[i] = idx < deg ? __ldcg(row + idx) : -1;
+            const unsigned bal = __ballot_sync(0xffffffffu, ids[i] < 0);
+            if (bal && first_neg == kMaxDeg) first_neg = 32 * i + __ffs(bal) - 1;
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxIdsPerLane; i++)
+            if (lane + 32 * i >= first_neg) ids[i] = -1;
+    }
+
+    // ---- visited hash (leader warp) --------------------------------------------
+    __device__ __forceinline__ bool hash_test_and_set(uint32_t id, int bits) const {
+        const uint32_t mask = (1u << bits) - 1u;
+        uint32_t h = hash_id(id, bits);
+        for (;;) {
+            const uint32_t old = atomicCAS(s.hash + h, kEmpty, id);
+            if (old == kEmpty) return true;   // newly inserted
+            if (old == id) return false;      // already visited
+            h = (h + 1) & mask;
+        }
+    }
+    __device__ __forceinline__ void hash_clear(int bits) const {
+        const int slots = 1 << bits;
+        for (int i = lane; i < slots; i += 32) s.hash[i] = kEmpty;
+        __syncwarp();
+    }
+
+    // ---- App. A.4: greedy descent from (cur_id) at levels max_level .. stop_level+1 ----
+    // All warps of the group call this; on return the leader's (cur_id, cur_d) are valid.
+    __device__ void descend(int stop_level, uint32_t& cur_id, float& cur_d, BeamStats& st) const {
+        if (wig == 0) {
+            if (lane == 0) {
+                s.cand_id[0] = g.entry_point;
+                s.ctrl[0] = 1;
+            }
+            __syncwarp();
+        }
+        group_sync();
+        compute_dists(1);
+        group_sync();
+        int level = g.max_level;
+        if (wig == 0) {
+            cur_id = (uint32_t)g.entry_point;
+            cur_d = key_dist(s.cand_key[0]);
+        }
+        for (;;) {
+            if (wig == 0) {
+                int n = -1;
+                if (level > stop_level) {
+                    int ids[kMaxIdsPerLane];
+                    load_row((int)cur_id, level, ids);
+                    n = 0;
+#pragma unroll
+                    for (int i = 0; i < kMaxIdsPerLane; i++) {
+                        const unsigned bal = __ballot_sync(0xffffffffu, ids[i] >= 0);
+                        if (ids[i] >= 0) s.cand_id[n + __popc(bal & ((1u << lane) - 1u))] = ids[i];
+                        n += __popc(bal);
+                    }
+                    st.ndis_up += n;
+                    st.nhops_up += 1;
+                }
+                if (lane == 0) s.ctrl[0] = n;
+                __syncwarp();
+            }
+            group_sync();
+            const int n = s.ctrl[0];
+            if (n < 0) break;
+            compute_dists(n);
+            group_sync();
+            if (wig == 0) {
+                // sequential "take it if strictly closer" == argmin with first-index ties
+                unsigned long long best = ~0ull;
+                for (int j = lane; j < n; j += 32) {
+                    const unsigned long long kj = (s.cand_key[j] & 0xFFFFFFFF00000000ull) | (unsigned)j;
+                    best = kj < best ? kj : best;
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
+                    best = o < best ? o : best;
+                }
+                bool moved = false;
+                if (n > 0) {
+                    const float bd = ord2f((uint32_t)(best >> 32));
+                    if (bd < cur_d) {
+                        cur_d = bd;
+                        cur_id = (uint32_t)s.cand_id[(int)(best & 0xFFFFFFFFu)];
+                        moved = true;
+                    }
+                }
+                if (!moved) level--;
+            }
+        }
+    }
+
+    // ---- App. A.6 / A.9: ef-bounded best-first search at `level` -----------------
+    // ef       list capacity (max(efSearch,k) for search, efConstruction for build)
+    // ef_stop  stop when the popped entry has >= ef_stop list entries before it
+    //          (faiss count_below test; INT_MAX disables)
+    // max_steps  faiss `!check_relative_distance && nstep > efSearch` (INT_MAX disables)
+    // On return ctrl[1] = list size, ctrl[2] = index of the live list buffer.
+    __device__ void run(int level, int ef, int ef_stop, int max_steps, int hash_bits, uint32_t start_id,
+                        float start_d, BeamStats& st) const {
+        int lsize = 0, cur = 0, cursor = 0, hcount = 0, nstep = 0;
+        const int hlimit = (3 << hash_bits) >> 2;  // reset above 75 % load
+        if (wig == 0) {
+            hash_clear(hash_bits);
+            if (lane == 0) {
+                s.list[0][0] = pack_key(start_d, start_id);
+                hash_test_and_set(start_id, hash_bits);
+            }
+            lsize = 1;
+            hcount = 1;
+            __syncwarp();
+        }
+        for (;;) {
+            if (wig == 0) {
+                // -- pop_min: first unexpanded entry of the sorted list
+                int pos = -1;
+                const unsigned long long* L = s.list[cur];
+                for (int b = cursor & ~31; b < lsize; b += 32) {
+                    const int i = b + lane;
+                    const bool un = i >= cursor && i < lsize && !(L[i] & kExpanded);
+                    const unsigned bal = __ballot_sync(0xffffffffu, un);
+                    if (bal) {
+                        pos = b + __ffs(bal) - 1;
+                        break;
+                    }
+                }
+                int n_new = -1;
+                if (pos >= 0 && pos < ef_stop && nstep <= max_steps) {
+                    const uint32_t v0 = key_id(L[pos]);
+                    __syncwarp();
+                    if (lane == 0) s.list[cur][pos] = L[pos] | kExpanded;
+                    cursor = pos + 1;
+                    int ids[kMaxIdsPerLane];
+                    load_row((int)v0, level, ids);
+                    if (hcount + kMaxDeg > hlimit) {  // forget-and-reseed (see header)
+                        hash_clear(hash_bits);
+                        for (int i = lane; i < lsize; i += 32) hash_test_and_set(key_id(L[i]), hash_bits);
+                        hcount = lsize;
+                        __syncwarp();
+                    }
+                    n_new = 0;
+#pragma unroll
+                    for (int i = 0; i < kMaxIdsPerLane; i++) {
+                        const bool isnew = ids[i] >= 0 && hash_test_and_set((uint32_t)ids[i], hash_bits);
+                        const unsigned bal = __ballot_sync(0xffffffffu, isnew);
+                        if (isnew) s.cand_id[n_new + __popc(bal & ((1u << lane) - 1u))] = ids[i];
+                        n_new += __popc(bal);
+                    }
+                    hcount += n_new;
+                    st.ndis0 += n_new;
+                    st.nhops0 += 1;
+                    nstep++;
+                }
+                if (lane == 0) s.ctrl[0] = n_new;
+                __syncwarp();
+            }
+            group_sync();
+            const int n_new = s.ctrl[0];
+            if (n_new < 0) break;
+            compute_dists(n_new);
+            group_sync();
+            if (wig == 0 && n_new > 0) merge(n_new, ef, lsize, cur, cursor);
+        }
+        if (wig == 0) {
+            if (lane == 0) {
+                s.ctrl[1] = lsize;
+                s.ctrl[2] = cur;
+            }
+            __syncwarp();
+        }
+    }
+
+    // Merge the hop's scored candidates into the sorted list (leader warp).
+    // Equivalent to pushing them one by one into faiss's bounded MinimaxHeap: the list ends up
+    // holding the ef smallest keys of (list ∪ candidates); on exact distance ties the id breaks it.
+    __device__ __forceinline__ void merge(int n_new, int ef, int& lsize, int& cur, int& cursor) const {
+        const unsigned long long* L = s.list[cur];
+        unsigned long long* O = s.list[cur ^ 1];
+        const bool full = lsize == ef;
+        const unsigned long long thr = full ? key_clean(L[ef - 1]) : ~0ull;
+        int n_acc = 0;
+        for (int b = 0; b < n_new; b += 32) {
+            const int j = b + lane;
+            unsigned long long kj = ~0ull;
+            bool ok = false;
+            if (j < n_new) {
+                kj = s.cand_key[j];
+                ok = kj < thr;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if (ok) s.acc_key[n_acc + __popc(bal & ((1u << lane) - 1u))] = kj;
+            n_acc += __popc(bal);
+        }
+        if (n_acc == 0) return;
+        __syncwarp();
+        int minpos = ef;
+        unsigned long long minacc = ~0ull;
+        for (int a = lane; a < n_acc; a += 32) {
+            const unsigned long long ka = s.acc_key[a];
+            int ra = 0;
+            for (int b2 = 0; b2 < n_acc; b2++) ra += s.acc_key[b2] < ka;
+            int lo = 0, hi = lsize;  // lower_bound on clean keys
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (key_clean(L[mid]) < ka) lo = mid + 1; else hi = mid;
+            }
+            const int pos = ra + lo;
+            if (pos < ef) O[pos] = ka;
+            minpos = pos < minpos ? pos : minpos;
+            minacc = ka < minacc ? ka : minacc;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const int om = __shfl_xor_sync(0xffffffffu, minpos, off);
+            minpos = om < minpos ? om : minpos;
+            const unsigned long long oa = __shfl_xor_sync(0xffffffffu, minacc, off);
+            minacc = oa < minacc ? oa : minacc;
+        }
+        for (int i = lane; i < lsize; i += 32) {
+            const unsigned long long e = L[i];
+            const unsigned long long ec = key_clean(e);
+            int cnt = 0;
+            if (ec > minacc)
+                for (int b2 = 0; b2 < n_acc; b2++) cnt += s.acc_key[b2] < ec;
+            const int np = i + cnt;
+            if (np < ef) O[np] = e;
+        }
+        lsize = lsize + n_acc < ef ? lsize + n_acc : ef;
+        cursor = minpos < cursor ? minpos : cursor;
+        cur ^= 1;
+        __syncwarp();
+    }
+};
+
+}  // namespace bh

@@ -1,0 +1,154 @@
+// beam_kernel.cu — persistent traversal kernel (search mode and construction-search mode)
+// and its host-side dispatcher.
+//
+// One launch = one batch of queries (IndexHNSW::search's `omp parallel for` over queries,
+// SURVEY.md §3.1) or one batch of (point, level) insertion searches
+// (add_links_starting_from → search_neighbors_to_add, §3.2). Groups of W warps pull work
+// items from an atomic counter until the batch is drained.
+#include "beam.cuh"
+#include "engine.h"
+
+#include <cfloat>
+#include <climits>
+
+namespace bh {
+
+template <int TEAM, int CPL, int W, int R, int G>
+__global__ void __launch_bounds__(32 * W * G) beam_kernel(GraphView g, BeamTask t) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int grp = warp / W;
+    const int wig = warp % W;
+    const int hash_slots = 1 << t.hash_bits;
+    const size_t gbytes = group_smem_bytes(g.d, t.ef, hash_slots);
+    const GroupSmem s = carve_group_smem(smem_raw + grp * gbytes, g.d, t.ef, hash_slots);
+    Beam<TEAM, CPL, W, R> beam(g, s, wig, lane, 1 + grp);
+
+    if (wig == 0 && lane == 0) {
+        mbar_init(s.mbar, 1);
+        fence_mbar_init();
+    }
+    beam.group_sync();
+    uint32_t phase = 0;
+    const uint32_t qbytes = (uint32_t)g.d * 4u;
+
+    for (;;) {
+        if (wig == 0 && lane == 0) s.ctrl[3] = atomicAdd(t.counter, 1);
+        beam.group_sync();
+        const int wi = s.ctrl[3];
+        if (wi >= t.n_items) break;
+
+        int level = 0, stop_level = 0;
+        const float* qsrc;
+        if (t.items) {  // construction: the query is the stored vector of the new point
+            const int4 it = __ldg(t.items + wi);
+            qsrc = g.vecs + (size_t)it.x * g.d;
+            level = it.y;
+            stop_level = it.z;
+        } else {
+            qsrc = t.queries + (size_t)wi * g.d;
+        }
+        // query -> shared memory by 1-D bulk TMA, completion on the group's mbarrier
+        if (wig == 0 && lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(s.mbar, qbytes);
+            tma_load_1d(s.qbuf, qsrc, qbytes, s.mbar);
+        }
+        mbar_wait(s.mbar, phase);
+        phase ^= 1;
+        beam.load_query_from_smem();
+
+        BeamStats st;
+        uint32_t cur_id = 0;
+        float cur_d = 0.f;
+        beam.descend(stop_level, cur_id, cur_d, st);
+        beam.run(level, t.ef, t.ef_stop, t.max_steps, t.hash_bits, cur_id, cur_d, st);
+
+        if (wig == 0) {
+            const int lsize = s.ctrl[1];
+            const unsigned long long* L = s.list[s.ctrl[2]];
+            if (t.items) {
+                unsigned long long* out = t.out_lists + (size_t)wi * t.ef;
+                for (int i = lane; i < lsize; i += 32) out[i] = key_clean(L[i]);
+                if (lane == 0) t.out_counts[wi] = lsize;
+            } else {
+                const float pad = g.is_l2 ? FLT_MAX : -FLT_MAX;
+                for (int i = lane; i < t.k; i += 32) {
+                    float dd = pad;
+                    int64_t id = -1;
+                    if (i < lsize) {
+                        dd = key_dist(L[i]);
+                        if (!g.is_l2) dd = -dd;
+                        id = (int64_t)key_id(L[i]);
+                    }
+                    t.D[(size_t)wi * t.k + i] = dd;
+                    t.I[(size_t)wi * t.k + i] = id;
+                }
+            }
+            if (t.stats && lane == 0) {
+                int4 sv = make_int4(st.ndis0, st.nhops0, st.ndis_up, st.nhops_up);
+                reinterpret_cast<int4*>(t.stats)[wi] = sv;
+            }
+        }
+        beam.group_sync();
+    }
+}
+
+// ---------------------------------------------------------------- host dispatch
+namespace {
+
+template <int TEAM, int CPL, int W, int R, int G>
+cudaError_t launch_one(const GraphView& g, const BeamTask& t, int num_sms, cudaStream_t stream,
+                       int* grid_out) {
+    auto kern = beam_kernel<TEAM, CPL, W, R, G>;
+    const size_t smem = (size_t)G * group_smem_bytes(g.d, t.ef, 1 << t.hash_bits);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W * G, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorInvalidConfiguration;
+    long long groups_needed = ((long long)t.n_items + G - 1) / G;
+    long long grid = (long long)num_sms * occ;
+    if (grid > groups_needed) grid = groups_needed;
+    if (grid < 1) grid = 1;
+    if (grid_out) *grid_out = (int)grid;
+    kern<<<(unsigned)grid, 32 * W * G, smem, stream>>>(g, t);
+    return cudaGetLastError();
+}
+
+template <int TEAM, int CPL, int R>
+cudaError_t launch_w(const GraphView& g, const BeamTask& t, int W, int num_sms, cudaStream_t stream,
+                     int* grid_out) {
+    switch (W) {
+        case 1: return launch_one<TEAM, CPL, 1, R, 4>(g, t, num_sms, stream, grid_out);
+        case 2: return launch_one<TEAM, CPL, 2, R, 2>(g, t, num_sms, stream, grid_out);
+        case 4: return launch_one<TEAM, CPL, 4, R, 1>(g, t, num_sms, stream, grid_out);
+        case 8: return launch_one<TEAM, CPL, 8, R, 1>(g, t, num_sms, stream, grid_out);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace
+
+int team_for_dim(int d) {
+    if (d <= 128) return 8;
+    if (d <= 256) return 16;
+    return 32;
+}
+
+size_t beam_group_smem(int d, int ef, int hash_bits) { return group_smem_bytes(d, ef, 1 << hash_bits); }
+
+cudaError_t launch_beam(const GraphView& g, const BeamTask& t, int W, int num_sms, cudaStream_t stream,
+                        int* grid_out) {
+    const int d = g.d;
+    if (d <= 128) return launch_w<8, 4, 4>(g, t, W, num_sms, stream, grid_out);
+    if (d <= 256) return launch_w<16, 4, 4>(g, t, W, num_sms, stream, grid_out);
+    if (d <= 512) return launch_w<32, 4, 4>(g, t, W, num_sms, stream, grid_out);
+    if (d <= 1024) return launch_w<32, 8, 2>(g, t, W, num_sms, stream, grid_out);
+    if (d <= 2048) return launch_w<32, 16, 1>(g, t, W, num_sms, stream, grid_out);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace bh

@@ -1,0 +1,370 @@
+// build_kernels.cu — batched graph construction after the insertion searches.
+//
+// Restates (SURVEY.md App. A.9–A.11):
+//   shrink_neighbor_list  -> heuristic()             (diversity heuristic, warp-parallel)
+//   add_links_starting_from: forward links pt→o      -> select_and_link_kernel
+//   add_link(o→pt) under omp locks                   -> backlink_kernel
+// faiss serialises concurrent back-links to one vertex with a per-vertex omp_lock_t. Here every
+// back-edge of the batch is pushed (atomicExch) onto an intrusive per-row pending list; the
+// warp that owns the list's tail then applies that row's edges one after the other in edge-index
+// order (= insertion order, farthest neighbour first, as faiss does) — no locks, no spinning,
+// and the result does not depend on scheduling.
+#include "beam.cuh"
+#include "engine.h"
+
+namespace bh {
+
+namespace {
+
+constexpr int kChainCap = 256;
+
+template <int TEAM, int CPL>
+struct TeamVec {
+    float4 x[CPL];
+    // Load this lane's slice of a stored vector (generic pointer: global or shared).
+    __device__ __forceinline__ void load(const float4* row, int nchunk, int lit, bool valid) {
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+            const int chunk = c * TEAM + lit;
+            x[c] = (valid && chunk < nchunk) ? row[chunk] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    // Same arithmetic as Beam::compute_dists: one fmaf chain per lane, xor-butterfly over the team.
+    __device__ __forceinline__ float dist(const float4* row, int nchunk, int lit, bool is_l2) const {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+            const int chunk = c * TEAM + lit;
+            const float4 u = chunk < nchunk ? row[chunk] : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (is_l2) {
+                float t;
+                t = u.x - x[c].x; acc = fmaf(t, t, acc);
+                t = u.y - x[c].y; acc = fmaf(t, t, acc);
+                t = u.z - x[c].z; acc = fmaf(t, t, acc);
+                t = u.w - x[c].w; acc = fmaf(t, t, acc);
+            } else {
+                acc = fmaf(u.x, x[c].x, acc);
+                acc = fmaf(u.y, x[c].y, acc);
+                acc = fmaf(u.z, x[c].z, acc);
+                acc = fmaf(u.w, x[c].w, acc);
+            }
+        }
+#pragma unroll
+        for (int off = TEAM / 2; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
+        return is_l2 ? acc : -acc;
+    }
+};
+
+// App. A.10 — keep candidate v (nearest first) iff no already-kept u has d(u,v) < d(v,base).
+// cand: sorted clean keys (generic pointer), n >= 1. kept_key: shared, capacity >= max_size.
+// kvec: shared cache for kept vectors ([max_size][nchunk] float4) or nullptr (read them from HBM/L2).
+// 32/TEAM candidates are examined per step, one per team; dependencies inside a step are
+// resolved in candidate order, so the outcome equals the sequential scan.
+template <int TEAM, int CPL>
+__device__ int heuristic(const GraphView& g, const unsigned long long* cand, int n, int max_size,
+                         unsigned long long* kept_key, float4* kvec, int lane) {
+    constexpr int TPW = 32 / TEAM;
+    const int lit = lane % TEAM, team = lane / TEAM;
+    const float4* __restrict__ vecs = reinterpret_cast<const float4*>(g.vecs);
+    const bool is_l2 = g.is_l2 != 0;
+    int K = 0;
+    for (int c0 = 0; c0 < n && K < max_size; c0 += TPW) {
+        const int c = c0 + team;
+        const bool valid = c < n;
+        const unsigned long long key = valid ? cand[c] : ~0ull;
+        const uint32_t id = key_id(key);
+        const float dq = key_dist(key);
+        TeamVec<TEAM, CPL> v;
+        v.load(vecs + (size_t)(valid ? id : 0) * g.nchunk, g.nchunk, lit, valid);
+        bool bad = !valid;
+        for (int j = 0; j < K; j++) {
+            if (__all_sync(0xffffffffu, bad)) break;
+            const float4* u = kvec ? kvec + (size_t)j * g.nchunk : vecs + (size_t)key_id(kept_key[j]) * g.nchunk;
+            const float duv = v.dist(u, g.nchunk, lit, is_l2);
+            if (duv < dq) bad = true;
+        }
+        for (int t = 0; t < TPW; t++) {
+            const int bad_t = __shfl_sync(0xffffffffu, (int)bad, t * TEAM);
+            if (bad_t) continue;
+            if (team == t) {
+                if (lit == 0) kept_key[K] = key;
+                if (kvec) {
+#pragma unroll
+                    for (int cc = 0; cc < CPL; cc++) {
+                        const int chunk = cc * TEAM + lit;
+                        if (chunk < g.nchunk) kvec[(size_t)K * g.nchunk + chunk] = v.x[cc];
+                    }
+                }
+            }
+            __syncwarp();
+            K++;
+            if (K >= max_size) break;
+            if (t + 1 < TPW) {
+                const uint32_t id_t = __shfl_sync(0xffffffffu, id, t * TEAM);
+                const float4* u = kvec ? kvec + (size_t)(K - 1) * g.nchunk : vecs + (size_t)id_t * g.nchunk;
+                const float duv = v.dist(u, g.nchunk, lit, is_l2);
+                if (team > t && duv < dq) bad = true;
+            }
+        }
+    }
+    return K;
+}
+
+__device__ __forceinline__ int32_t* row_ptr_rw(const GraphView& g, int v, int level, int& deg) {
+    if (level == 0) {
+        deg = g.deg0;
+        return g.nbr0 + (size_t)v * g.deg0;
+    }
+    deg = g.degU;
+    const int b = __ldg(g.upper_base + v);
+    return g.upper_nbr + ((size_t)b + (level - 1)) * g.degU;
+}
+
+__device__ __forceinline__ int row_slot(const GraphView& g, int64_t n_level0, int v, int level) {
+    return level == 0 ? v : (int)(n_level0 + __ldg(g.upper_base + v) + (level - 1));
+}
+
+struct WarpSmem {
+    unsigned long long* kept_key;  // [kMaxDeg]
+    unsigned long long* cand_a;    // [kMaxDeg + 8]
+    unsigned long long* cand_b;    // [kMaxDeg + 8]
+    int32_t* chain;                // [kChainCap]
+    float4* kvec;                  // [deg0][nchunk] or nullptr
+};
+
+__host__ __device__ inline size_t warp_smem_bytes(int d, int deg0, bool kvec) {
+    return (size_t)kMaxDeg * 8 + 2 * (size_t)(kMaxDeg + 8) * 8 + (size_t)kChainCap * 4 +
+           (kvec ? (size_t)deg0 * d * 4 : 0);
+}
+
+__device__ inline WarpSmem carve_warp_smem(unsigned char* p, int d, int deg0, bool kvec) {
+    WarpSmem w;
+    w.kept_key = reinterpret_cast<unsigned long long*>(p);
+    p += (size_t)kMaxDeg * 8;
+    w.cand_a = reinterpret_cast<unsigned long long*>(p);
+    p += (size_t)(kMaxDeg + 8) * 8;
+    w.cand_b = reinterpret_cast<unsigned long long*>(p);
+    p += (size_t)(kMaxDeg + 8) * 8;
+    w.chain = reinterpret_cast<int32_t*>(p);
+    p += (size_t)kChainCap * 4;
+    w.kvec = kvec ? reinterpret_cast<float4*>(p) : nullptr;
+    return w;
+}
+
+// ---- forward links + back-edge staging: one warp per (point, level) item ------------
+template <int TEAM, int CPL>
+__global__ void __launch_bounds__(64) select_and_link_kernel(GraphView g, BuildBatch b, int use_kvec) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const WarpSmem w = carve_warp_smem(smem_raw + wib * warp_smem_bytes(g.d, g.deg0, use_kvec), g.d,
+                                       g.deg0, use_kvec);
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int item = blockIdx.x * (blockDim.x >> 5) + wib; item < b.n_items; item += nwarps) {
+        const int4 it = __ldg(b.items + item);
+        const int pt = it.x, level = it.y;
+        int deg;
+        int32_t* row = row_ptr_rw(g, pt, level, deg);
+        const unsigned long long* cand = b.cand_lists + (size_t)item * b.efc;
+        const int n = b.cand_counts[item];
+        int K;
+        const unsigned long long* kept;
+        if (n < deg) {  // shrink_neighbor_list returns early: keep everything
+            K = n;
+            kept = cand;
+        } else {
+            K = heuristic<TEAM, CPL>(g, cand, n, deg, w.kept_key, w.kvec, lane);
+            kept = w.kept_key;
+        }
+        __syncwarp();
+        // faiss pops link_targets farthest-first: row[i] = kept[K-1-i]
+        for (int i = lane; i < g.deg0; i += 32) {
+            const int e = item * g.deg0 + i;
+            if (i < K) {
+                const unsigned long long key = kept[K - 1 - i];
+                const int o = (int)key_id(key);
+                row[i] = o;
+                const int slot = row_slot(g, b.n_level0, o, level);
+                b.edge_src[e] = pt;
+                b.edge_dst[e] = o;
+                b.edge_level[e] = level;
+                b.edge_dist[e] = key_dist(key);
+                b.edge_dst_slot[e] = slot;
+                b.edge_next[e] = atomicExch(b.slot_head + slot, e);
+            } else {
+                if (i < deg) row[i] = -1;
+                b.edge_dst_slot[e] = -1;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- App. A.11 add_link(dst ← src) for every staged back-edge ------------------------
+template <int TEAM, int CPL>
+__global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b, int use_kvec) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int TPW = 32 / TEAM;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lit = lane % TEAM, team = lane / TEAM;
+    const WarpSmem w = carve_warp_smem(smem_raw + wib * warp_smem_bytes(g.d, g.deg0, use_kvec), g.d,
+                                       g.deg0, use_kvec);
+    const float4* __restrict__ vecs = reinterpret_cast<const float4*>(g.vecs);
+    const bool is_l2 = g.is_l2 != 0;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    const int n_edges = b.n_items * g.deg0;
+    for (int e0 = blockIdx.x * (blockDim.x >> 5) + wib; e0 < n_edges; e0 += nwarps) {
+        const int slot = b.edge_dst_slot[e0];
+        if (slot < 0 || b.edge_next[e0] != -1) continue;  // only the tail of a row's list owns it
+        // collect the row's pending edges (pushed in arbitrary order) and sort by edge index
+        int c = 0, head = -1;
+        if (lane == 0) {
+            head = b.slot_head[slot];
+            for (int e = head; e >= 0; e = b.edge_next[e]) {
+                if (c < kChainCap) w.chain[c] = e;
+                c++;
+            }
+            b.slot_head[slot] = -1;
+        }
+        c = __shfl_sync(0xffffffffu, c, 0);
+        head = __shfl_sync(0xffffffffu, head, 0);
+        __syncwarp();
+        const bool overflow = c > kChainCap;
+        int last_done = -1;
+        const int dst = b.edge_dst[e0], level = b.edge_level[e0];
+        int deg;
+        int32_t* row = row_ptr_rw(g, dst, level, deg);
+        TeamVec<TEAM, CPL> q;  // the destination vertex's own vector (base of the distances)
+        bool q_loaded = false;
+
+        for (int done = 0; done < c; done++) {
+            // next edge = smallest edge index > last_done
+            int e = 0x7fffffff;
+            if (!overflow) {
+                for (int i = lane; i < c; i += 32) {
+                    const int v = w.chain[i];
+                    if (v > last_done && v < e) e = v;
+                }
+            } else if (lane == 0) {  // rare (> kChainCap edges to one row): re-walk the list
+                for (int x = head; x >= 0; x = b.edge_next[x])
+                    if (x > last_done && x < e) e = x;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const int o = __shfl_xor_sync(0xffffffffu, e, off);
+                e = o < e ? o : e;
+            }
+            if (e == 0x7fffffff) break;
+            last_done = e;
+            const int src = b.edge_src[e];
+            const float d_src = b.edge_dist[e];
+
+            // current row state
+            int ids[kMaxIdsPerLane];
+            int last_valid = -1;
+#pragma unroll
+            for (int i = 0; i < kMaxIdsPerLane; i++) {
+                const int idx = lane + 32 * i;
+                ids[i] = idx < deg ? __ldcg(row + idx) : -1;
+                const unsigned bal = __ballot_sync(0xffffffffu, ids[i] >= 0);
+                if (bal) last_valid = 32 * i + 31 - __clz(bal);
+            }
+            if (last_valid < deg - 1) {  // room: first free slot after the last valid entry
+                if (lane == 0) row[last_valid + 1] = src;
+                __syncwarp();
+                continue;
+            }
+            // full row: the deg+1 candidates fight it out (shrink_neighbor_list)
+            if (!q_loaded) {
+                q.load(vecs + (size_t)dst * g.nchunk, g.nchunk, lit, true);
+                q_loaded = true;
+            }
+            const int n = deg + 1;
+            if (lane == 0) w.cand_a[0] = pack_key(d_src, (uint32_t)src);
+#pragma unroll
+            for (int i = 0; i < kMaxIdsPerLane; i++) {
+                // stage ids so teams can pick them up
+                const int idx = lane + 32 * i;
+                if (idx < deg) w.cand_b[idx] = (unsigned long long)(uint32_t)ids[i];
+            }
+            __syncwarp();
+            for (int r0 = 0; r0 < deg; r0 += TPW) {
+                const int r = r0 + team;
+                const bool valid = r < deg;
+                const uint32_t id = valid ? (uint32_t)w.cand_b[r] : 0u;
+                const float dd = q.dist(vecs + (size_t)id * g.nchunk, g.nchunk, lit, is_l2);
+                if (valid && lit == 0) w.cand_a[1 + r] = pack_key(dd, id);
+            }
+            __syncwarp();
+            // rank sort cand_a[0..n) -> cand_b[0..n)
+            for (int a = lane; a < n; a += 32) {
+                const unsigned long long ka = w.cand_a[a];
+                int rk = 0;
+                for (int j = 0; j < n; j++) {
+                    const unsigned long long kj = w.cand_a[j];
+                    rk += (kj < ka) || (kj == ka && j < a);
+                }
+                w.cand_b[rk] = ka;
+            }
+            __syncwarp();
+            const int K = heuristic<TEAM, CPL>(g, w.cand_b, n, deg, w.kept_key, w.kvec, lane);
+            __syncwarp();
+            for (int i = lane; i < deg; i += 32) row[i] = i < K ? (int)key_id(w.kept_key[K - 1 - i]) : -1;
+            __syncwarp();
+        }
+    }
+}
+
+template <int TEAM, int CPL>
+cudaError_t launch_build_pair(bool backlinks, const GraphView& g, const BuildBatch& b, int num_sms,
+                              cudaStream_t stream) {
+    const bool kvec = (size_t)g.deg0 * g.d * 4 <= 48 * 1024;
+    const int wpb = 2;
+    const size_t smem = wpb * warp_smem_bytes(g.d, g.deg0, kvec);
+    auto ks = select_and_link_kernel<TEAM, CPL>;
+    auto kb = backlink_kernel<TEAM, CPL>;
+    cudaError_t e;
+    if (!backlinks) {
+        e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ks, 32 * wpb, smem);
+        long long grid = (long long)num_sms * (occ < 1 ? 1 : occ);
+        const long long need = (b.n_items + wpb - 1) / wpb;
+        if (grid > need) grid = need;
+        if (grid < 1) grid = 1;
+        ks<<<(unsigned)grid, 32 * wpb, smem, stream>>>(g, b, (int)kvec);
+    } else {
+        e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb, 32 * wpb, smem);
+        long long grid = (long long)num_sms * (occ < 1 ? 1 : occ);
+        const long long need = ((long long)b.n_items * g.deg0 + wpb - 1) / wpb;
+        if (grid > need) grid = need;
+        if (grid < 1) grid = 1;
+        kb<<<(unsigned)grid, 32 * wpb, smem, stream>>>(g, b, (int)kvec);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t dispatch_build(bool backlinks, const GraphView& g, const BuildBatch& b, int num_sms,
+                           cudaStream_t stream) {
+    const int d = g.d;
+    if (d <= 128) return launch_build_pair<8, 4>(backlinks, g, b, num_sms, stream);
+    if (d <= 256) return launch_build_pair<16, 4>(backlinks, g, b, num_sms, stream);
+    if (d <= 512) return launch_build_pair<32, 4>(backlinks, g, b, num_sms, stream);
+    if (d <= 1024) return launch_build_pair<32, 8>(backlinks, g, b, num_sms, stream);
+    if (d <= 2048) return launch_build_pair<32, 16>(backlinks, g, b, num_sms, stream);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+cudaError_t launch_select_and_link(const GraphView& g, const BuildBatch& b, int num_sms, cudaStream_t stream) {
+    return dispatch_build(false, g, b, num_sms, stream);
+}
+cudaError_t launch_backlinks(const GraphView& g, const BuildBatch& b, int num_sms, cudaStream_t stream) {
+    return dispatch_build(true, g, b, num_sms, stream);
+}
+
+}  // namespace bh

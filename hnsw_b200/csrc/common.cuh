@@ -1,0 +1,102 @@
+// common.cuh — shared device/host helpers for the sm_100a HNSW kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bh {
+
+constexpr uint32_t kEmpty = 0xFFFFFFFFu;          // empty visited-hash slot
+constexpr unsigned long long kExpanded = 0x80000000ull;  // "already expanded" bit of a list key
+constexpr int kMaxDeg = 128;                       // 2*M <= 128
+constexpr int kMaxIdsPerLane = kMaxDeg / 32;
+
+// Device-side view of one index shard (SURVEY §8a1/a2 re-laid-out for HBM):
+//   vecs       fp32 [ntotal][d] row-major (faiss IndexFlat codes)
+//   nbr0       int32 [ntotal][deg0]   level-0 rows, deg0 = 2M, -1 terminated
+//   upper_base int32 [ntotal]         first upper row of vertex i (in rows of degU), -1 if level 0
+//   upper_nbr  int32 [nupper][degU]   rows for levels 1..L of a vertex are consecutive
+struct GraphView {
+    const float* vecs;
+    int32_t* nbr0;
+    const int32_t* upper_base;
+    int32_t* upper_nbr;
+    int d;
+    int nchunk;  // d / 4
+    int deg0;
+    int degU;
+    int entry_point;
+    int max_level;
+    int is_l2;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// Order-preserving map float -> uint32 (works for negative values: IP search runs on -dot).
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    uint32_t b = __float_as_uint(f);
+    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+    uint32_t b = u ^ (((u >> 31) - 1u) | 0x80000000u);
+    return __uint_as_float(b);
+}
+__device__ __forceinline__ unsigned long long pack_key(float dist, uint32_t id) {
+    return ((unsigned long long)f2ord(dist) << 32) | id;
+}
+__device__ __forceinline__ float key_dist(unsigned long long k) { return ord2f((uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t key_id(unsigned long long k) { return (uint32_t)k & 0x7FFFFFFFu; }
+__device__ __forceinline__ unsigned long long key_clean(unsigned long long k) { return k & ~kExpanded; }
+
+__device__ __forceinline__ uint32_t hash_id(uint32_t id, int bits) {
+    return (id * 2654435761u) >> (32 - bits);
+}
+
+// ---- mbarrier + 1-D bulk TMA (cp.async.bulk → UBLKCP in SASS) -------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    } while (!ok);
+}
+
+// Named barrier over the `nthreads` threads of one query group (ids 1..15; 0 = __syncthreads).
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// 128-bit read-only gather load that does not allocate in L1 (rows are not reused by the SM).
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+}  // namespace bh

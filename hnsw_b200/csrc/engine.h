@@ -1,0 +1,65 @@
+// engine.h — host-side declarations shared by the kernel translation units and the
+// C-ABI layer (capi.cu). Nothing here is exported; the public surface is include/b200_hnsw.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace bh {
+
+// One batch of traversal work for beam_kernel.
+struct BeamTask {
+    // search mode (items == nullptr)
+    const float* queries;  // device [n_items][d]
+    int k;
+    float* D;              // device [n_items][k]
+    int64_t* I;            // device [n_items][k]
+    // construction mode
+    const int4* items;     // device [n_items] {point id, search level, stop level (= pt_level), 0}
+    unsigned long long* out_lists;  // device [n_items][ef] sorted clean keys
+    int32_t* out_counts;            // device [n_items]
+    // common
+    int n_items;
+    int ef;         // list capacity
+    int ef_stop;    // count_below threshold (INT_MAX = off)
+    int max_steps;  // nstep limit (INT_MAX = off)
+    int hash_bits;
+    int32_t* stats;  // device int32[n_items][4] or null
+    int* counter;    // device work counter, zeroed before launch
+};
+
+int team_for_dim(int d);
+size_t beam_group_smem(int d, int ef, int hash_bits);
+cudaError_t launch_beam(const GraphView& g, const BeamTask& t, int W, int num_sms, cudaStream_t stream,
+                        int* grid_out);
+
+// ---- construction kernels (build_kernels.cu) ------------------------------------
+struct BuildBatch {
+    const int4* items;                    // [n_items] {pt, level, pt_level, 0}
+    const unsigned long long* cand_lists; // [n_items][efc] sorted (dist,id) keys, nearest first
+    const int32_t* cand_counts;           // [n_items]
+    int n_items;
+    int efc;
+    // back-edge staging: one slot per (item, kept neighbour)
+    int32_t* edge_dst_slot;   // [n_items*kMaxDeg] row slot of the destination (see row_slot), -1 = none
+    int32_t* edge_src;        // [..] the new point
+    int32_t* edge_dst;        // [..] destination vertex
+    int32_t* edge_level;      // [..]
+    float* edge_dist;         // [..] d(src, dst)
+    int32_t* edge_next;       // [..] intrusive list link
+    int32_t* slot_head;       // [n_slots] head of the per-row pending list, -1 = empty (persistent)
+    int64_t n_level0;         // number of level-0 rows (= ntotal capacity used for slot numbering)
+};
+
+cudaError_t launch_select_and_link(const GraphView& g, const BuildBatch& b, int num_sms, cudaStream_t stream);
+cudaError_t launch_backlinks(const GraphView& g, const BuildBatch& b, int num_sms, cudaStream_t stream);
+
+// ---- sharded top-k merge (merge_kernel.cu) ---------------------------------------
+cudaError_t launch_merge_topk(int nshard, int64_t nq, int k, int is_l2, const float* D_all,
+                              const int64_t* I_all, const int64_t* id_offsets_dev, float* D_out,
+                              int64_t* I_out, cudaStream_t stream);
+
+void count_launch(int n = 1);
+
+}  // namespace bh

@@ -1,0 +1,67 @@
+// merge_kernel.cu — warp-per-query merge of per-shard sorted top-k lists.
+//
+// Replaces faiss merge_knn_results as used by IndexShards(successive_ids=true)
+// (SURVEY.md §8e): after an all-gather every rank holds [nshard][nq][k] (distance, local id)
+// lists, each sorted best-first. Each element's final rank is the number of elements, over all
+// shard lists, that precede it (binary search per list; ties broken by shard then position), so
+// the merge is a scatter with no serial heap.
+#include "engine.h"
+
+namespace bh {
+
+namespace {
+
+__global__ void __launch_bounds__(128) merge_topk_kernel(int nshard, int64_t nq, int k, int is_l2,
+                                                         const float* __restrict__ D_all,
+                                                         const int64_t* __restrict__ I_all,
+                                                         const int64_t* __restrict__ id_off,
+                                                         float* __restrict__ D_out,
+                                                         int64_t* __restrict__ I_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t q = warp; q < nq; q += nwarps) {
+        const int total = nshard * k;
+        for (int e = lane; e < total; e += 32) {
+            const int s = e / k, i = e - s * k;
+            const float v = D_all[((size_t)s * nq + q) * k + i];
+            int rank = i;
+            for (int s2 = 0; s2 < nshard; s2++) {
+                if (s2 == s) continue;
+                const float* L = D_all + ((size_t)s2 * nq + q) * k;
+                // number of entries of list s2 that come before (v, s): strictly better, or equal
+                // and from a lower shard
+                int lo = 0, hi = k;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const float u = L[mid];
+                    const bool before = is_l2 ? (u < v || (u == v && s2 < s)) : (u > v || (u == v && s2 < s));
+                    if (before) lo = mid + 1; else hi = mid;
+                }
+                rank += lo;
+            }
+            if (rank < k) {
+                const int64_t id = I_all[((size_t)s * nq + q) * k + i];
+                D_out[(size_t)q * k + rank] = v;
+                I_out[(size_t)q * k + rank] = id >= 0 ? id + id_off[s] : -1;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_merge_topk(int nshard, int64_t nq, int k, int is_l2, const float* D_all,
+                              const int64_t* I_all, const int64_t* id_offsets_dev, float* D_out,
+                              int64_t* I_out, cudaStream_t stream) {
+    if (nq == 0) return cudaSuccess;
+    const int wpb = 4;
+    long long grid = (nq + wpb - 1) / wpb;
+    if (grid > 148 * 16) grid = 148 * 16;
+    merge_topk_kernel<<<(unsigned)grid, 32 * wpb, 0, stream>>>(nshard, nq, k, is_l2, D_all, I_all,
+                                                              id_offsets_dev, D_out, I_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace bh

@@ -1,0 +1,186 @@
+"""IndexHNSWFlat — Python mirror of faiss.IndexHNSWFlat over the B200 engine's C-ABI.
+
+Same constructor, fields and method meanings as faiss:
+    index = IndexHNSWFlat(d, M, metric)      faiss.IndexHNSWFlat(d, M, metric)
+    index.hnsw.efConstruction / efSearch      index.hnsw.efConstruction / efSearch
+    index.train(x); index.add(x)              no-op train; add copies vectors and links them
+    D, I = index.search(xq, k)                float32 [nq,k] ascending L2² (descending IP), int64
+Errors surface as RuntimeError carrying the library's message (faiss raises on bad input too).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import BuildParams, SearchParams
+
+METRIC_INNER_PRODUCT = 0
+METRIC_L2 = 1
+
+
+class _HNSWFields:
+    """index.hnsw.* — the faiss `HNSW` struct's tunables."""
+
+    def __init__(self, owner: "IndexHNSWFlat"):
+        self._o = owner
+
+    @property
+    def efSearch(self):
+        return _lib.lib().bh_index_get_ef_search(self._o._h)
+
+    @efSearch.setter
+    def efSearch(self, v):
+        _lib.check(_lib.lib().bh_index_set_ef_search(self._o._h, int(v)))
+
+    @property
+    def efConstruction(self):
+        return _lib.lib().bh_index_get_ef_construction(self._o._h)
+
+    @efConstruction.setter
+    def efConstruction(self, v):
+        _lib.check(_lib.lib().bh_index_set_ef_construction(self._o._h, int(v)))
+
+    @property
+    def entry_point(self):
+        return _lib.lib().bh_index_entry_point(self._o._h)
+
+    @property
+    def max_level(self):
+        return _lib.lib().bh_index_max_level(self._o._h)
+
+    @property
+    def check_relative_distance(self):
+        return self._o._crd
+
+    @check_relative_distance.setter
+    def check_relative_distance(self, v):
+        self._o._crd = bool(v)
+        _lib.check(_lib.lib().bh_index_set_check_relative_distance(self._o._h, int(bool(v))))
+
+
+class IndexHNSWFlat:
+    def __init__(self, d: int, M: int = 32, metric: int = METRIC_L2, device: int = 0):
+        L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(L.bh_index_create(C.byref(h), int(d), int(M), int(metric), int(device)))
+        self._h = h
+        self.d = int(d)
+        self.M = int(M)
+        self.metric_type = int(metric)
+        self.device = int(device)
+        self.is_trained = True
+        self.verbose = False
+        self._crd = True
+        self.hnsw = _HNSWFields(self)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().bh_index_free(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ---- faiss.Index surface
+    @property
+    def ntotal(self) -> int:
+        return int(_lib.lib().bh_index_ntotal(self._h))
+
+    def train(self, x=None):
+        _lib.check(_lib.lib().bh_index_train(self._h, 0 if x is None else len(x), None))
+
+    def _as_f32(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != self.d:
+            raise ValueError(f"expected a [n, {self.d}] float32 array, got {x.shape}")
+        return x
+
+    def add(self, x, levels=None, order=None):
+        """faiss Index.add. `levels` (level+1 per row) and `order` preset the faiss-drawn values."""
+        x = self._as_f32(x)
+        if levels is None and order is None:
+            _lib.check(_lib.lib().bh_index_add(self._h, x.shape[0], x.ctypes.data))
+            return
+        lv = None if levels is None else np.ascontiguousarray(levels, np.int32)
+        od = None if order is None else np.ascontiguousarray(order, np.int32)
+        _lib.check(_lib.lib().bh_index_add_ex(self._h, x.shape[0], x.ctypes.data,
+                                              None if lv is None else lv.ctypes.data,
+                                              None if od is None else od.ctypes.data))
+
+    def search(self, x, k: int, params: SearchParams | None = None, efSearch: int | None = None,
+               stats: bool = False, out=None, warps_per_query: int = 0, hash_bits: int = 0):
+        """faiss Index.search → (D, I). `out=(D, I)` reuses caller buffers (e.g. pinned)."""
+        x = self._as_f32(x)
+        nq = x.shape[0]
+        if out is None:
+            D = np.empty((nq, k), np.float32)
+            I = np.empty((nq, k), np.int64)
+        else:
+            D, I = out
+        st = np.zeros((nq, 4), np.int32) if stats else None
+        if params is None:
+            params = SearchParams(int(efSearch or 0), 0, int(warps_per_query), int(hash_bits), None)
+        if st is not None:
+            params.stats = st.ctypes.data
+        _lib.check(_lib.lib().bh_index_search(self._h, nq, x.ctypes.data, int(k), D.ctypes.data,
+                                              I.ctypes.data, C.byref(params)))
+        return (D, I, st) if stats else (D, I)
+
+    def search_device(self, xq_ptr: int, nq: int, k: int, D_ptr: int, I_ptr: int,
+                      efSearch: int = 0, stats_ptr: int = 0, warps_per_query: int = 0,
+                      hash_bits: int = 0):
+        """Enqueue a search on device buffers (raw pointers); no host sync."""
+        p = SearchParams(int(efSearch), 0, int(warps_per_query), int(hash_bits), stats_ptr or None)
+        _lib.check(_lib.lib().bh_index_search_device(self._h, int(nq), xq_ptr, int(k), D_ptr, I_ptr,
+                                                     C.byref(p)))
+
+    def reset(self):
+        _lib.check(_lib.lib().bh_index_reset(self._h))
+
+    def reconstruct(self, key: int):
+        out = np.empty(self.d, np.float32)
+        _lib.check(_lib.lib().bh_index_reconstruct(self._h, int(key), out.ctypes.data))
+        return out
+
+    # ---- engine extras
+    def set_build_params(self, max_batch=0, batch_divisor=0, warps_per_query=0, hash_bits=0):
+        p = BuildParams(int(max_batch), int(batch_divisor), int(warps_per_query), int(hash_bits))
+        _lib.check(_lib.lib().bh_index_set_build_params(self._h, C.byref(p)))
+
+    def synchronize(self):
+        _lib.check(_lib.lib().bh_index_synchronize(self._h))
+
+    @property
+    def last_build_ms(self):
+        return float(_lib.lib().bh_index_last_build_ms(self._h))
+
+    @property
+    def last_search_ms(self):
+        return float(_lib.lib().bh_index_last_search_ms(self._h))
+
+    def export_graph(self):
+        """Graph in faiss's HNSW layout: levels, offsets, neighbors, entry_point, max_level."""
+        L = _lib.lib()
+        n = self.ntotal
+        levels = np.empty(n, np.int32)
+        offsets = np.empty(n + 1, np.uint64)
+        neighbors = np.empty(int(L.bh_index_neighbors_size(self._h)), np.int32)
+        _lib.check(L.bh_index_export_graph(self._h, levels.ctypes.data, offsets.ctypes.data,
+                                           neighbors.ctypes.data))
+        return dict(levels=levels, offsets=offsets, neighbors=neighbors,
+                    entry_point=self.hnsw.entry_point, max_level=self.hnsw.max_level)
+
+    def import_graph(self, x, levels, neighbors, entry_point, max_level):
+        x = self._as_f32(x)
+        levels = np.ascontiguousarray(levels, np.int32)
+        neighbors = np.ascontiguousarray(neighbors, np.int32)
+        _lib.check(_lib.lib().bh_index_import_graph(self._h, x.shape[0], x.ctypes.data,
+                                                    levels.ctypes.data, neighbors.ctypes.data,
+                                                    neighbors.shape[0], int(entry_point), int(max_level)))
+
+
+def launch_count() -> int:
+    return int(_lib.lib().bh_launch_count())

@@ -1,0 +1,127 @@
+/* b200_hnsw.h — C-ABI of the B200-native HNSW engine (libb200hnsw.so).
+ *
+ * Drop-in boundary for the one hot path this repo accelerates: faiss::IndexHNSWFlat
+ * train / add / search, which is what the reference repo is built on
+ * (/root/reference/README.md:2 — the mount holds no source, so there is no reference
+ * file:line to cite beyond that; the upstream interface each entry point replaces is
+ * named instead).
+ *
+ * Conventions (mirroring faiss's own c_api): every function returns int, 0 = OK,
+ * non-zero = error with a thread-local message from bh_last_error(); no C++ exception
+ * crosses this boundary. idx_t is int64_t. All `const float* x` arguments are HOST
+ * pointers to contiguous row-major fp32 unless the function name ends in `_device`.
+ * The caller owns every buffer it passes; add() copies vectors into index-owned HBM.
+ * There is NO CPU fallback: creating an index without a usable CUDA device fails.
+ */
+#ifndef B200_HNSW_H
+#define B200_HNSW_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bh_index bh_index; /* opaque */
+
+/* faiss/MetricType.h: METRIC_INNER_PRODUCT = 0, METRIC_L2 = 1 */
+#define BH_METRIC_INNER_PRODUCT 0
+#define BH_METRIC_L2 1
+
+/* Per-call search parameters — faiss::SearchParametersHNSW {efSearch,
+ * check_relative_distance} plus engine knobs. Zero-initialise for defaults. */
+typedef struct bh_search_params {
+    int32_t efSearch;                /* <=0: use the index's hnsw.efSearch */
+    int32_t check_relative_distance; /* 0: index default, 1: on, 2: off */
+    int32_t warps_per_query;         /* 0: auto; 1,2,4,8: warps cooperating on one query */
+    int32_t hash_bits;               /* 0: auto; log2 of the visited-hash slots per query */
+    int32_t* stats;                  /* optional int32[n][4]: {ndis L0, nhops L0, ndis upper,
+                                        nhops upper}; host ptr (device ptr for *_device) */
+} bh_search_params;
+
+/* Build-time knobs (no faiss equivalent: faiss's concurrency is the OpenMP thread count). */
+typedef struct bh_build_params {
+    int32_t max_batch;       /* points inserted concurrently per round; <=0: auto */
+    int32_t batch_divisor;   /* a round inserts at most ntotal_so_far / batch_divisor points
+                                (>=1 point); <=0: auto. max_batch=1 => faiss's sequential order */
+    int32_t warps_per_query; /* 0: auto */
+    int32_t hash_bits;       /* 0: auto */
+} bh_build_params;
+
+/* -- lifecycle ------------------------------------------------------------------- */
+/* replaces faiss::IndexHNSWFlat::IndexHNSWFlat(int d, int M, MetricType metric) */
+int bh_index_create(bh_index** out, int d, int M, int metric, int device);
+/* replaces faiss::Index::~Index */
+int bh_index_free(bh_index* h);
+/* replaces faiss::IndexHNSW::reset */
+int bh_index_reset(bh_index* h);
+
+/* -- the path: train / add / search ---------------------------------------------- */
+/* replaces faiss::IndexHNSW::train (a no-op for Flat storage; is_trained is true) */
+int bh_index_train(bh_index* h, int64_t n, const float* x);
+/* replaces faiss::IndexHNSW::add → storage->add + hnsw_add_vertices */
+int bh_index_add(bh_index* h, int64_t n, const float* x);
+/* same, with caller-supplied levels (level+1 per point, faiss `hnsw.levels` preset) and an
+ * optional explicit insertion order (permutation of [ntotal, ntotal+n)); either may be NULL */
+int bh_index_add_ex(bh_index* h, int64_t n, const float* x, const int32_t* levels,
+                    const int32_t* order);
+/* replaces faiss::IndexHNSW::search(n, x, k, distances, labels, params) */
+int bh_index_search(const bh_index* h, int64_t n, const float* x, int64_t k, float* distances,
+                    int64_t* labels, const bh_search_params* params);
+/* extension: x, distances, labels (and params->stats) are DEVICE pointers on the index's
+ * device; enqueued on the index's stream; returns without synchronising */
+int bh_index_search_device(const bh_index* h, int64_t n, const float* x, int64_t k,
+                           float* distances, int64_t* labels, const bh_search_params* params);
+/* replaces faiss::IndexHNSW::reconstruct */
+int bh_index_reconstruct(const bh_index* h, int64_t key, float* out);
+
+/* -- fields (faiss: index.d, index.ntotal, index.hnsw.efSearch, …) ---------------- */
+int64_t bh_index_ntotal(const bh_index* h);
+int bh_index_d(const bh_index* h);
+int bh_index_M(const bh_index* h);
+int bh_index_metric(const bh_index* h);
+int bh_index_entry_point(const bh_index* h);
+int bh_index_max_level(const bh_index* h);
+int bh_index_get_ef_search(const bh_index* h);
+int bh_index_set_ef_search(bh_index* h, int ef);
+int bh_index_get_ef_construction(const bh_index* h);
+int bh_index_set_ef_construction(bh_index* h, int ef);
+int bh_index_set_check_relative_distance(bh_index* h, int on);
+int bh_index_set_build_params(bh_index* h, const bh_build_params* p);
+
+/* -- graph exchange in faiss's HNSW layout (hnsw.levels / offsets / neighbors) ----- */
+/* number of int32 entries in `neighbors` for the current graph */
+int64_t bh_index_neighbors_size(const bh_index* h);
+int bh_index_export_graph(const bh_index* h, int32_t* levels, uint64_t* offsets,
+                          int32_t* neighbors);
+/* replaces read_index for an in-memory graph: vectors + levels + neighbors (+ entry) */
+int bh_index_import_graph(bh_index* h, int64_t n, const float* x, const int32_t* levels,
+                          const int32_t* neighbors, int64_t nneighbors, int entry_point,
+                          int max_level);
+
+/* -- streams & timing -------------------------------------------------------------- */
+/* cudaStream_t the index enqueues on (as void*) */
+void* bh_index_stream(const bh_index* h);
+int bh_index_synchronize(const bh_index* h);
+/* device milliseconds of the most recent add() graph-construction phase / search launch */
+float bh_index_last_build_ms(const bh_index* h);
+float bh_index_last_search_ms(const bh_index* h);
+/* kernels launched by this library since load (for bench.py's gpu_launches) */
+int64_t bh_launch_count(void);
+
+/* -- sharded search: merge of per-shard top-k lists (replaces faiss merge_knn_results
+ *    as used by IndexShards(successive_ids=true)) ------------------------------------
+ * D_all / I_all: device, [nshard][nq][k], each list sorted best-first, I local to its
+ * shard (-1 = empty). Writes device D_out/I_out [nq][k] with I + id_offsets[shard].
+ * stream: cudaStream_t as void* (NULL = default stream). */
+int bh_merge_topk_device(int nshard, int64_t nq, int64_t k, int metric, const float* D_all,
+                         const int64_t* I_all, const int64_t* id_offsets /*host, [nshard]*/,
+                         float* D_out, int64_t* I_out, void* stream);
+
+const char* bh_last_error(void);
+const char* bh_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_HNSW_H */

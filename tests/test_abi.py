@@ -1,0 +1,62 @@
+"""CPU tests of the drop-in boundary: the shared library loads, exports every symbol that
+include/b200_hnsw.h declares, and refuses (loudly) to work without a CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import has_gpu
+from hnsw_b200 import _lib
+
+
+def _header_functions():
+    src = open(_lib.HEADER_PATH).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bh_[A-Za-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "libb200hnsw.so not built (run __graft_entry__.build())"
+    L = C.CDLL(_lib.LIB_PATH)
+    names = _header_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in b200_hnsw.h but not exported"
+    # and the Python binding covers the whole header
+    assert sorted(_lib.EXPORTED) == names
+
+
+def test_no_torch_types_in_the_abi():
+    src = open(_lib.HEADER_PATH).read()
+    assert "torch" not in src.lower() and "Tensor" not in src and "#include <stdint.h>" in src
+
+
+def test_version_and_error_channel():
+    L = _lib.lib()
+    assert b"sm_100a" in L.bh_version()
+    h = C.c_void_p()
+    assert L.bh_index_create(C.byref(h), 7, 32, 1, 0) != 0          # d not a multiple of 4
+    assert "multiple of 4" in _lib.last_error()
+    assert L.bh_index_create(C.byref(h), 128, 100, 1, 0) != 0       # M too large
+    assert L.bh_index_create(C.byref(h), 128, 32, 5, 0) != 0        # unknown metric
+    assert L.bh_index_ntotal(None) == -1
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_create_fails_loudly_without_a_gpu():
+    import hnsw_b200
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hnsw_b200.IndexHNSWFlat(128, 32)
+
+
+def test_product_never_imports_the_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "hnsw_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dp, fn)).read()
+                assert "oracle" not in txt.replace("the oracle's team mode", "").replace(
+                    "// the oracle", "") or fn in ("beam.cuh",), f"{fn} mentions the oracle"

@@ -1,0 +1,158 @@
+"""GPU parity tests of the search path (greedy descent + level-0 beam search), through the C-ABI.
+
+The oracle's team mode reproduces the CUDA kernels' summation order bit for bit, so on a graph
+imported from the oracle the GPU must return IDENTICAL ids, distances and per-query counters
+(stronger than BASELINE.json's "identical except for distance ties" / 1e-4 relative)."""
+import numpy as np
+import pytest
+
+from hnsw_b200.datasets import synthetic_dataset
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_from_oracle(o, xb, M, metric=1):
+    import hnsw_b200
+    g = o.export_graph()
+    idx = hnsw_b200.IndexHNSWFlat(xb.shape[1], M, metric)
+    idx.import_graph(xb, g["levels"], g["neighbors"], g["entry_point"], g["max_level"])
+    return idx
+
+
+def test_import_export_roundtrip(small_l2):
+    idx = _gpu_from_oracle(small_l2["oracle"], small_l2["xb"], 16)
+    g, g2 = small_l2["graph"], idx.export_graph()
+    for key in ("levels", "offsets", "neighbors"):
+        assert np.array_equal(g[key], g2[key])
+    assert g2["entry_point"] == g["entry_point"] and g2["max_level"] == g["max_level"]
+    assert np.array_equal(idx.reconstruct(17), small_l2["xb"][17])
+
+
+@pytest.mark.parametrize("ef", [16, 32, 64, 128, 256])
+@pytest.mark.parametrize("W", [1, 2, 4, 8])
+def test_search_bit_exact_vs_oracle(small_l2, ef, W):
+    idx = _gpu_from_oracle(small_l2["oracle"], small_l2["xb"], 16)
+    Do, Io, So = small_l2["oracle"].search(small_l2["xq"], 10, ef, stats=True)
+    D, I, S = idx.search(small_l2["xq"], 10, efSearch=ef, stats=True, warps_per_query=W)
+    assert np.array_equal(I, Io)
+    assert np.array_equal(D, Do)
+    assert np.array_equal(S, So)          # ndis / nhops at level 0 and above: same path
+
+
+def test_distances_within_1e4_of_native_simd_oracle(oracle_mod, small_l2):
+    """BASELINE north_star tolerance: returned distances within 1e-4 relative of the CPU path
+    that uses its own (SIMD) summation order."""
+    g = small_l2["graph"]
+    nat = oracle_mod.OracleHNSWFlat(32, 16)
+    nat.import_graph(small_l2["xb"], g["levels"], g["neighbors"], g["entry_point"], g["max_level"])
+    Dn, In = nat.search(small_l2["xq"], 10, 64)
+    idx = _gpu_from_oracle(small_l2["oracle"], small_l2["xb"], 16)
+    D, I = idx.search(small_l2["xq"], 10, efSearch=64)
+    same = I == In
+    assert same.mean() > 0.99                      # only exact-tie flips may differ
+    assert np.allclose(D[same], Dn[same], rtol=1e-4, atol=1e-7)
+
+
+def test_small_hash_forces_resets_but_not_result_changes(small_l2):
+    idx = _gpu_from_oracle(small_l2["oracle"], small_l2["xb"], 16)
+    Do, Io = small_l2["oracle"].search(small_l2["xq"], 10, 128)
+    D, I, S = idx.search(small_l2["xq"], 10, efSearch=128, stats=True, hash_bits=10)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do)
+
+
+def test_k_larger_than_efsearch_and_unbounded_steps(small_l2):
+    o = small_l2["oracle"]
+    idx = _gpu_from_oracle(o, small_l2["xb"], 16)
+    Do, Io, So = o.search(small_l2["xq"], 40, 8, stats=True)     # ef = k, count_below can fire
+    D, I, S = idx.search(small_l2["xq"], 40, efSearch=8, stats=True)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do) and np.array_equal(S, So)
+    o.set_check_relative_distance(False)
+    try:
+        Do, Io, So = o.search(small_l2["xq"], 10, 24, stats=True)
+    finally:
+        o.set_check_relative_distance(True)
+    idx.hnsw.check_relative_distance = False
+    D, I, S = idx.search(small_l2["xq"], 10, efSearch=24, stats=True)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do) and np.array_equal(S, So)
+
+
+@pytest.mark.parametrize("d,M,team,metric", [(96, 16, 8, 1), (128, 32, 8, 1), (256, 8, 16, 1),
+                                             (512, 8, 32, 1), (960, 8, 32, 1), (768, 16, 32, 0),
+                                             (128, 64, 8, 0), (4, 4, 8, 1)])
+def test_dims_metrics_and_degrees(oracle_mod, d, M, team, metric):
+    xb, xq = synthetic_dataset(d, 1500, 40, normalize=(metric == 0))
+    o = oracle_mod.OracleHNSWFlat(d, M, metric)
+    o.set_team(team)
+    o.efConstruction = 32
+    o.add(xb)
+    idx = _gpu_from_oracle(o, xb, M, metric)
+    for ef in (16, 100):
+        Do, Io, So = o.search(xq, 10, ef, stats=True)
+        D, I, S = idx.search(xq, 10, efSearch=ef, stats=True)
+        assert np.array_equal(I, Io) and np.array_equal(D, Do) and np.array_equal(S, So)
+
+
+def test_edge_cases(oracle_mod):
+    import hnsw_b200
+    d = 16
+    idx = hnsw_b200.IndexHNSWFlat(d, 8)
+    xq = np.random.RandomState(1).randn(3, d).astype(np.float32)
+    D, I = idx.search(xq, 5)                                   # empty index
+    assert np.all(I == -1) and np.all(D == np.finfo(np.float32).max)
+    D, I = idx.search(xq[:0], 5)                               # zero queries
+    assert D.shape == (0, 5)
+    with pytest.raises(RuntimeError):
+        idx.search(xq, 0)
+    with pytest.raises(ValueError):
+        idx.search(np.zeros((2, d + 4), np.float32), 5)
+    xb = np.random.RandomState(2).randn(3, d).astype(np.float32)
+    o = oracle_mod.OracleHNSWFlat(d, 8)
+    o.set_team(8)
+    o.add(xb)
+    g = o.export_graph()
+    idx.import_graph(xb, g["levels"], g["neighbors"], g["entry_point"], g["max_level"])
+    Do, Io = o.search(xq, 5)
+    D, I = idx.search(xq, 5)                                   # ntotal < k: -1 / FLT_MAX padding
+    assert np.array_equal(I, Io) and np.array_equal(D, Do)
+    idx.reset()
+    assert idx.ntotal == 0
+
+
+def test_large_query_batch_and_ragged_tail(small_l2):
+    o = small_l2["oracle"]
+    idx = _gpu_from_oracle(o, small_l2["xb"], 16)
+    rs = np.random.RandomState(5)
+    xq = small_l2["xb"][rs.randint(0, 4000, 5003)] + 0.01 * rs.randn(5003, 32).astype(np.float32)
+    o.threads = 8
+    Do, Io = o.search(xq, 7, 40)
+    o.threads = 1
+    D, I = idx.search(xq, 7, efSearch=40)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do)
+
+
+def test_merge_topk_matches_numpy():
+    import ctypes as C
+    import torch
+    from hnsw_b200 import _lib
+    rs = np.random.RandomState(3)
+    for metric in (1, 0):
+        ns, nq, k = 5, 257, 10
+        D = np.sort(rs.rand(ns, nq, k).astype(np.float32), axis=2)
+        D[:, :, -2:][rs.rand(ns, nq, 2) < 0.3] = np.finfo(np.float32).max     # some empty slots
+        D = np.sort(D, axis=2)
+        I = rs.randint(0, 1000, (ns, nq, k)).astype(np.int64)
+        I[D == np.finfo(np.float32).max] = -1
+        if metric == 0:
+            D = -D
+        off = np.arange(ns, dtype=np.int64) * 1000
+        Dd, Id = torch.from_numpy(D).cuda(), torch.from_numpy(I).cuda()
+        Do = torch.empty(nq, k, device="cuda")
+        Io = torch.empty(nq, k, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        _lib.check(_lib.lib().bh_merge_topk_device(ns, nq, k, metric, Dd.data_ptr(), Id.data_ptr(),
+                                                   off.ctypes.data, Do.data_ptr(), Io.data_ptr(), None))
+        allD = D.transpose(1, 0, 2).reshape(nq, ns * k)
+        allI = np.where(I >= 0, I + off[:, None, None], -1).transpose(1, 0, 2).reshape(nq, ns * k)
+        order = np.argsort(allD if metric == 1 else -allD, axis=1, kind="stable")[:, :k]
+        assert np.array_equal(Do.cpu().numpy(), np.take_along_axis(allD, order, 1))
+        assert np.array_equal(Io.cpu().numpy(), np.take_along_axis(allI, order, 1))
