@@ -186,10 +186,15 @@ struct Beam {
     __device__ __forceinline__ bool hash_test_and_set(uint32_t id, int bits) const {
         const uint32_t mask = (1u << bits) - 1u;
         uint32_t h = hash_id(id, bits);
+        volatile uint32_t* tab = s.hash;
         for (;;) {
-            const uint32_t old = atomicCAS(s.hash + h, kEmpty, id);
-            if (old == kEmpty) return true;   // newly inserted
-            if (old == id) return false;      // already visited
+            const uint32_t cur = tab[h];       // plain probe first: a CAS only on an empty slot
+            if (cur == id) return false;       // already visited
+            if (cur == kEmpty) {
+                const uint32_t old = atomicCAS(s.hash + h, kEmpty, id);
+                if (old == kEmpty) return true;  // newly inserted
+                if (old == id) return false;
+            }
             h = (h + 1) & mask;
         }
     }
@@ -309,7 +314,7 @@ struct Beam {
                     cursor = pos + 1;
                     int ids[kMaxIdsPerLane];
                     load_row((int)v0, level, ids);
-                    if (hcount + kMaxDeg > hlimit) {  // forget-and-reseed (see header)
+                    if (hcount + (level == 0 ? g.deg0 : g.degU) > hlimit) {  // forget-and-reseed (see header)
                         hash_clear(hash_bits);
                         for (int i = lane; i < lsize; i += 32) hash_test_and_set(key_id(L[i]), hash_bits);
                         hcount = lsize;

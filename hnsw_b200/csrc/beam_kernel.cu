@@ -13,8 +13,8 @@
 
 namespace bh {
 
-template <int TEAM, int CPL, int W, int R, int G>
-__global__ void __launch_bounds__(32 * W * G) beam_kernel(GraphView g, BeamTask t) {
+template <int TEAM, int CPL, int W, int R, int G, int MINB>
+__global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, BeamTask t) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -98,10 +98,10 @@ __global__ void __launch_bounds__(32 * W * G) beam_kernel(GraphView g, BeamTask 
 // ---------------------------------------------------------------- host dispatch
 namespace {
 
-template <int TEAM, int CPL, int W, int R, int G>
+template <int TEAM, int CPL, int W, int R, int G, int MINB>
 cudaError_t launch_one(const GraphView& g, const BeamTask& t, int num_sms, cudaStream_t stream,
                        int* grid_out) {
-    auto kern = beam_kernel<TEAM, CPL, W, R, G>;
+    auto kern = beam_kernel<TEAM, CPL, W, R, G, MINB>;
     const size_t smem = (size_t)G * group_smem_bytes(g.d, t.ef, 1 << t.hash_bits);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -118,14 +118,20 @@ cudaError_t launch_one(const GraphView& g, const BeamTask& t, int num_sms, cudaS
     return cudaGetLastError();
 }
 
+// variant (W == 1 only): 0 = R rows in flight per team, 4 blocks/SM (<=128 regs);
+// 1 = R/2 rows, 6 blocks/SM (<=80 regs); 2 = R/2 rows, 8 blocks/SM (<=64 regs).
 template <int TEAM, int CPL, int R>
-cudaError_t launch_w(const GraphView& g, const BeamTask& t, int W, int num_sms, cudaStream_t stream,
-                     int* grid_out) {
+cudaError_t launch_w(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
+                     cudaStream_t stream, int* grid_out) {
+    constexpr int RH = R >= 2 ? R / 2 : 1;
     switch (W) {
-        case 1: return launch_one<TEAM, CPL, 1, R, 4>(g, t, num_sms, stream, grid_out);
-        case 2: return launch_one<TEAM, CPL, 2, R, 2>(g, t, num_sms, stream, grid_out);
-        case 4: return launch_one<TEAM, CPL, 4, R, 1>(g, t, num_sms, stream, grid_out);
-        case 8: return launch_one<TEAM, CPL, 8, R, 1>(g, t, num_sms, stream, grid_out);
+        case 1:
+            if (variant == 1) return launch_one<TEAM, CPL, 1, RH, 4, 6>(g, t, num_sms, stream, grid_out);
+            if (variant == 2) return launch_one<TEAM, CPL, 1, RH, 4, 8>(g, t, num_sms, stream, grid_out);
+            return launch_one<TEAM, CPL, 1, R, 4, 4>(g, t, num_sms, stream, grid_out);
+        case 2: return launch_one<TEAM, CPL, 2, R, 2, 1>(g, t, num_sms, stream, grid_out);
+        case 4: return launch_one<TEAM, CPL, 4, R, 1, 1>(g, t, num_sms, stream, grid_out);
+        case 8: return launch_one<TEAM, CPL, 8, R, 1, 1>(g, t, num_sms, stream, grid_out);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -140,14 +146,14 @@ int team_for_dim(int d) {
 
 size_t beam_group_smem(int d, int ef, int hash_bits) { return group_smem_bytes(d, ef, 1 << hash_bits); }
 
-cudaError_t launch_beam(const GraphView& g, const BeamTask& t, int W, int num_sms, cudaStream_t stream,
-                        int* grid_out) {
+cudaError_t launch_beam(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
+                        cudaStream_t stream, int* grid_out) {
     const int d = g.d;
-    if (d <= 128) return launch_w<8, 4, 4>(g, t, W, num_sms, stream, grid_out);
-    if (d <= 256) return launch_w<16, 4, 4>(g, t, W, num_sms, stream, grid_out);
-    if (d <= 512) return launch_w<32, 4, 4>(g, t, W, num_sms, stream, grid_out);
-    if (d <= 1024) return launch_w<32, 8, 2>(g, t, W, num_sms, stream, grid_out);
-    if (d <= 2048) return launch_w<32, 16, 1>(g, t, W, num_sms, stream, grid_out);
+    if (d <= 128) return launch_w<8, 4, 4>(g, t, W, variant, num_sms, stream, grid_out);
+    if (d <= 256) return launch_w<16, 4, 4>(g, t, W, variant, num_sms, stream, grid_out);
+    if (d <= 512) return launch_w<32, 4, 4>(g, t, W, variant, num_sms, stream, grid_out);
+    if (d <= 1024) return launch_w<32, 8, 2>(g, t, W, variant, num_sms, stream, grid_out);
+    if (d <= 2048) return launch_w<32, 16, 1>(g, t, W, variant, num_sms, stream, grid_out);
     return cudaErrorInvalidValue;
 }
 

@@ -10,6 +10,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <string>
@@ -151,18 +152,29 @@ struct bh_index {
         return (int)assign_probas.size() - 1;
     }
 
+    // Visited-hash slots per query. The table is "forgetful" (beam.cuh), so its size is a pure
+    // performance knob: small tables keep many queries resident per SM at the price of a few
+    // re-scored vertices. Minimum: 3/4 of the slots must hold the ef-list plus one full row.
+    int min_hash_bits(int ef) const { return std::max(8, ceil_log2(((long long)(ef + deg0()) * 4 + 2) / 3 + 1)); }
     int auto_hash_bits(int ef, int req) const {
-        if (req > 0) return std::min(std::max(req, 8), 16);
-        int b = ceil_log2((long long)(0.6 * ef * deg0()) + 1);
-        return std::min(std::max(b, 10), 15);
+        const int lo = min_hash_bits(ef);
+        if (req > 0) return std::min(std::max(req, lo), 16);
+        int b = ceil_log2((long long)ef * 8);
+        b = std::max(b, 10);
+        return std::min(std::max(b, lo), 15);
     }
     int auto_warps(int ef, int hash_bits, int req) const {
         if (req == 1 || req == 2 || req == 4 || req == 8) return req;
+        // one warp per query keeps the most queries in flight; go wider only when a single
+        // query's state no longer fits beside three others in one SM's shared memory
         const size_t s = bh::beam_group_smem(d, ef, hash_bits);
-        if (s <= 14 * 1024) return 1;
-        if (s <= 28 * 1024) return 2;
-        if (s <= 56 * 1024) return 4;
-        return 8;
+        if (4 * s <= smem_optin) return 1;
+        if (2 * s <= smem_optin) return 2;
+        return 4;
+    }
+    static int beam_variant() {
+        const char* e = getenv("BH_BEAM_VARIANT");
+        return e ? atoi(e) : 0;
     }
 
     int ensure_capacity(int64_t n_new_total, int64_t upper_rows_total) {
@@ -207,7 +219,6 @@ int search_device_impl(const bh_index* h, int64_t n, const float* xq_d, int64_t 
     const int ef = (int)std::max<int64_t>(efS, k);
     if (ef > 4096) return fail("max(efSearch, k) > 4096 is not supported");
     const int hb = h->auto_hash_bits(ef, params ? params->hash_bits : 0);
-    if ((1 << hb) * 3 / 4 < ef + 2 * bh::kMaxDeg) return fail("hash_bits too small for this efSearch");
     const int W = h->auto_warps(ef, hb, params ? params->warps_per_query : 0);
     const int G = W >= 4 ? 1 : 4 / W;
     if (G * bh::beam_group_smem(h->d, ef, hb) > h->smem_optin)
@@ -226,7 +237,7 @@ int search_device_impl(const bh_index* h, int64_t n, const float* xq_d, int64_t 
     t.stats = stats_d;
     t.counter = h->counter.p;
     BH_CUDA(cudaMemsetAsync(h->counter.p, 0, sizeof(int), h->stream));
-    BH_CUDA(bh::launch_beam(h->view(), t, W, h->num_sms, h->stream, nullptr));
+    BH_CUDA(bh::launch_beam(h->view(), t, W, bh_index::beam_variant(), h->num_sms, h->stream, nullptr));
     bh::count_launch();
     return 0;
 }
@@ -327,7 +338,7 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     //    start of the round (faiss's OpenMP build has the same blindness between the points its
     //    threads are inserting at one moment). Rounds are kept small relative to the graph.
     const int max_batch = h->bp.max_batch > 0 ? h->bp.max_batch : 8192;
-    const int divisor = h->bp.batch_divisor > 0 ? h->bp.batch_divisor : 16;
+    const int divisor = h->bp.batch_divisor > 0 ? h->bp.batch_divisor : 64;
     struct Round { int64_t item_begin, item_end; int new_entry, new_max_level; };
     std::vector<int4> items;
     std::vector<Round> rounds;
@@ -377,7 +388,6 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     const int efc = h->efConstruction;
     if (efc < 1 || efc > 4096) return fail("efConstruction must be in [1, 4096]");
     const int hb = h->auto_hash_bits(efc, h->bp.hash_bits);
-    if ((1 << hb) * 3 / 4 < efc + 2 * bh::kMaxDeg) return fail("hash_bits too small for efConstruction");
     const int W = h->auto_warps(efc, hb, h->bp.warps_per_query);
     const int G = W >= 4 ? 1 : 4 / W;
     if (G * bh::beam_group_smem(d, efc, hb) > h->smem_optin)
@@ -413,7 +423,7 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
             t.stats = nullptr;
             t.counter = h->counter.p;
             BH_CUDA(cudaMemsetAsync(h->counter.p, 0, sizeof(int), h->stream));
-            BH_CUDA(bh::launch_beam(g, t, W, h->num_sms, h->stream, nullptr));
+            BH_CUDA(bh::launch_beam(g, t, W, bh_index::beam_variant(), h->num_sms, h->stream, nullptr));
             bh::BuildBatch b{};
             b.items = t.items;
             b.cand_lists = h->cand_lists.p;

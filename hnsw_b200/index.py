@@ -150,6 +150,11 @@ class IndexHNSWFlat:
         p = BuildParams(int(max_batch), int(batch_divisor), int(warps_per_query), int(hash_bits))
         _lib.check(_lib.lib().bh_index_set_build_params(self._h, C.byref(p)))
 
+    @property
+    def stream_ptr(self) -> int:
+        """cudaStream_t (as an integer) the index enqueues its kernels on."""
+        return int(_lib.lib().bh_index_stream(self._h) or 0)
+
     def synchronize(self):
         _lib.check(_lib.lib().bh_index_synchronize(self._h))
 
@@ -184,3 +189,13 @@ class IndexHNSWFlat:
 
 def launch_count() -> int:
     return int(_lib.lib().bh_launch_count())
+
+
+def merge_topk_device(D_all_ptr: int, I_all_ptr: int, nshard: int, nq: int, k: int, metric: int,
+                      id_offsets, D_out_ptr: int, I_out_ptr: int, stream_ptr: int = 0):
+    """Warp top-k merge of per-shard sorted lists (device pointers); see bh_merge_topk_device."""
+    import numpy as np
+    off = np.ascontiguousarray(id_offsets, np.int64)
+    _lib.check(_lib.lib().bh_merge_topk_device(int(nshard), int(nq), int(k), int(metric), D_all_ptr,
+                                               I_all_ptr, off.ctypes.data, D_out_ptr, I_out_ptr,
+                                               stream_ptr or None))

@@ -64,7 +64,7 @@ def test_sequential_build_in_two_add_calls(oracle_mod):
 @pytest.mark.parametrize("metric", [1, 0])
 def test_batched_build_invariants_and_recall(oracle_mod, metric):
     d, M, efc, n = 64, 16, 64, 20000
-    xb, xq = synthetic_dataset(d, n, 200, d1=16, normalize=(metric == 0))
+    xb, xq = synthetic_dataset(d, n, 2000, d1=12, normalize=(metric == 0))
     _, gt = oracle_mod.brute_force_knn(xb, xq, 10, metric)
     o = oracle_mod.OracleHNSWFlat(d, M, metric)
     o.efConstruction = efc

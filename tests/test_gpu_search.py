@@ -33,10 +33,15 @@ def test_import_export_roundtrip(small_l2):
 def test_search_bit_exact_vs_oracle(small_l2, ef, W):
     idx = _gpu_from_oracle(small_l2["oracle"], small_l2["xb"], 16)
     Do, Io, So = small_l2["oracle"].search(small_l2["xq"], 10, ef, stats=True)
-    D, I, S = idx.search(small_l2["xq"], 10, efSearch=ef, stats=True, warps_per_query=W)
+    # hash_bits=14: the visited table never fills, so the distance-evaluation counts match too
+    D, I, S = idx.search(small_l2["xq"], 10, efSearch=ef, stats=True, warps_per_query=W, hash_bits=13)
     assert np.array_equal(I, Io)
     assert np.array_equal(D, Do)
     assert np.array_equal(S, So)          # ndis / nhops at level 0 and above: same path
+    # default (small, forgetful) table: identical results, hop count identical, ndis may only grow
+    D, I, S = idx.search(small_l2["xq"], 10, efSearch=ef, stats=True, warps_per_query=W)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do)
+    assert np.array_equal(S[:, 1:], So[:, 1:]) and np.all(S[:, 0] >= So[:, 0])
 
 
 def test_distances_within_1e4_of_native_simd_oracle(oracle_mod, small_l2):
@@ -56,15 +61,16 @@ def test_distances_within_1e4_of_native_simd_oracle(oracle_mod, small_l2):
 def test_small_hash_forces_resets_but_not_result_changes(small_l2):
     idx = _gpu_from_oracle(small_l2["oracle"], small_l2["xb"], 16)
     Do, Io = small_l2["oracle"].search(small_l2["xq"], 10, 128)
-    D, I, S = idx.search(small_l2["xq"], 10, efSearch=128, stats=True, hash_bits=10)
-    assert np.array_equal(I, Io) and np.array_equal(D, Do)
+    for hb in (8, 9, 10):
+        D, I, S = idx.search(small_l2["xq"], 10, efSearch=128, stats=True, hash_bits=hb)
+        assert np.array_equal(I, Io) and np.array_equal(D, Do)
 
 
 def test_k_larger_than_efsearch_and_unbounded_steps(small_l2):
     o = small_l2["oracle"]
     idx = _gpu_from_oracle(o, small_l2["xb"], 16)
     Do, Io, So = o.search(small_l2["xq"], 40, 8, stats=True)     # ef = k, count_below can fire
-    D, I, S = idx.search(small_l2["xq"], 40, efSearch=8, stats=True)
+    D, I, S = idx.search(small_l2["xq"], 40, efSearch=8, stats=True, hash_bits=13)
     assert np.array_equal(I, Io) and np.array_equal(D, Do) and np.array_equal(S, So)
     o.set_check_relative_distance(False)
     try:
@@ -72,7 +78,7 @@ def test_k_larger_than_efsearch_and_unbounded_steps(small_l2):
     finally:
         o.set_check_relative_distance(True)
     idx.hnsw.check_relative_distance = False
-    D, I, S = idx.search(small_l2["xq"], 10, efSearch=24, stats=True)
+    D, I, S = idx.search(small_l2["xq"], 10, efSearch=24, stats=True, hash_bits=13)
     assert np.array_equal(I, Io) and np.array_equal(D, Do) and np.array_equal(S, So)
 
 
@@ -88,8 +94,10 @@ def test_dims_metrics_and_degrees(oracle_mod, d, M, team, metric):
     idx = _gpu_from_oracle(o, xb, M, metric)
     for ef in (16, 100):
         Do, Io, So = o.search(xq, 10, ef, stats=True)
-        D, I, S = idx.search(xq, 10, efSearch=ef, stats=True)
+        D, I, S = idx.search(xq, 10, efSearch=ef, stats=True, hash_bits=13)
         assert np.array_equal(I, Io) and np.array_equal(D, Do) and np.array_equal(S, So)
+        D, I = idx.search(xq, 10, efSearch=ef)
+        assert np.array_equal(I, Io) and np.array_equal(D, Do)
 
 
 def test_edge_cases(oracle_mod):
