@@ -38,7 +38,7 @@ METRIC_NAME = "QPS at recall@10>=0.95 (1M x128 L2)"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=1_000_000)
@@ -69,47 +69,60 @@ def bytes_per_query(stats, d, M, k):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region (NVML, every 10 ms)."""
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
+        self.sm, self.reasons, self.max_sm = [], set(), None
         self._stop = threading.Event()
         self._t = None
+        self._nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nv = pynvml
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _sample(self):
+        nv = self._nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(
+            nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+                          ("hw_thermal_slowdown", 0x40), ("hw_power_brake_slowdown", 0x80)):
+            if r & bit:
+                self.reasons.add(name)
 
     def _run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self._sample()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.01)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        if self._nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self._t:
+            self._t.join(timeout=2)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for j, n in enumerate(names) if any(r[3 + j] == "Active" for r in self.rows if len(r) > 3 + j)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["clock sampling unavailable"]}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def make_data(a, seed):

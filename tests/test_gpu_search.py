@@ -164,3 +164,28 @@ def test_merge_topk_matches_numpy():
         order = np.argsort(allD if metric == 1 else -allD, axis=1, kind="stable")[:, :k]
         assert np.array_equal(Do.cpu().numpy(), np.take_along_axis(allD, order, 1))
         assert np.array_equal(Io.cpu().numpy(), np.take_along_axis(allI, order, 1))
+
+
+def test_sharded_index_single_rank_nccl(small_l2):
+    """The NCCL code path of ShardedIndexHNSWFlat on a 1-rank group equals the plain index."""
+    import socket
+    import torch
+    import torch.distributed as dist
+    import hnsw_b200
+    from hnsw_b200.sharded import ShardedIndexHNSWFlat
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1, device_id=dev)
+    try:
+        sh = ShardedIndexHNSWFlat(32, 16, 1, device=dev)
+        sh.add(small_l2["xb"])
+        ref = hnsw_b200.IndexHNSWFlat(32, 16)
+        ref.add(small_l2["xb"])
+        D, I = sh.search(small_l2["xq"], 10, efSearch=64)
+        torch.cuda.synchronize()
+        Dr, Ir = ref.search(small_l2["xq"], 10, efSearch=64)
+        assert np.array_equal(I.cpu().numpy(), Ir) and np.array_equal(D.cpu().numpy(), Dr)
+        assert sh.ntotal == 4000
+    finally:
+        dist.destroy_process_group()
