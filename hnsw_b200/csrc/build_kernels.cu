@@ -16,7 +16,7 @@ namespace bh {
 
 namespace {
 
-constexpr int kChainCap = 256;
+constexpr int kChainCap = 64;
 
 template <int TEAM, int CPL>
 struct TeamVec {
@@ -53,42 +53,114 @@ struct TeamVec {
         for (int off = TEAM / 2; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
         return is_l2 ? acc : -acc;
     }
+    // Four independent pairs at once (same per-pair arithmetic; the four fmaf chains interleave).
+    __device__ __forceinline__ void dist4(const float4* r0, const float4* r1, const float4* r2,
+                                          const float4* r3, int nchunk, int lit, bool is_l2,
+                                          float (&out)[4]) const {
+        const float4* rows[4] = {r0, r1, r2, r3};
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+            const int chunk = c * TEAM + lit;
+            float4 u[4];
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                u[p] = chunk < nchunk ? rows[p][chunk] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                if (is_l2) {
+                    float t;
+                    t = u[p].x - x[c].x; acc[p] = fmaf(t, t, acc[p]);
+                    t = u[p].y - x[c].y; acc[p] = fmaf(t, t, acc[p]);
+                    t = u[p].z - x[c].z; acc[p] = fmaf(t, t, acc[p]);
+                    t = u[p].w - x[c].w; acc[p] = fmaf(t, t, acc[p]);
+                } else {
+                    acc[p] = fmaf(u[p].x, x[c].x, acc[p]);
+                    acc[p] = fmaf(u[p].y, x[c].y, acc[p]);
+                    acc[p] = fmaf(u[p].z, x[c].z, acc[p]);
+                    acc[p] = fmaf(u[p].w, x[c].w, acc[p]);
+                }
+            }
+        }
+#pragma unroll
+        for (int off = TEAM / 2; off >= 1; off >>= 1) {
+#pragma unroll
+            for (int p = 0; p < 4; p++) acc[p] = acc[p] + __shfl_xor_sync(0xffffffffu, acc[p], off);
+        }
+#pragma unroll
+        for (int p = 0; p < 4; p++) out[p] = is_l2 ? acc[p] : -acc[p];
+    }
 };
 
 // App. A.10 — keep candidate v (nearest first) iff no already-kept u has d(u,v) < d(v,base).
 // cand: sorted clean keys (generic pointer), n >= 1. kept_key: shared, capacity >= max_size.
-// kvec: shared cache for kept vectors ([max_size][nchunk] float4) or nullptr (read them from HBM/L2).
+// Two vector sources:
+//   STAGED = false: candidate vectors come from HBM/L2 (the next group of 32/TEAM candidates is
+//                   prefetched into registers while the current group is tested); kept vectors are
+//                   cached in shared memory `kvec` ([max_size][nchunk] float4) when it is non-null.
+//   STAGED = true : every candidate vector already sits in shared memory `stage` at slot
+//                   cand_slot[c]; kept vectors are read back from their slots (kept_slot[]).
 // 32/TEAM candidates are examined per step, one per team; dependencies inside a step are
 // resolved in candidate order, so the outcome equals the sequential scan.
-template <int TEAM, int CPL>
+template <int TEAM, int CPL, bool STAGED>
 __device__ int heuristic(const GraphView& g, const unsigned long long* cand, int n, int max_size,
-                         unsigned long long* kept_key, float4* kvec, int lane) {
+                         unsigned long long* kept_key, float4* kvec, const float4* stage,
+                         const int32_t* cand_slot, int32_t* kept_slot, int lane) {
     constexpr int TPW = 32 / TEAM;
     const int lit = lane % TEAM, team = lane / TEAM;
     const float4* __restrict__ vecs = reinterpret_cast<const float4*>(g.vecs);
     const bool is_l2 = g.is_l2 != 0;
     int K = 0;
-    for (int c0 = 0; c0 < n && K < max_size; c0 += TPW) {
+    TeamVec<TEAM, CPL> nxt;
+    unsigned long long nxt_key = ~0ull;
+    int nxt_slot = 0;
+    auto fetch = [&](int c0) {
         const int c = c0 + team;
         const bool valid = c < n;
-        const unsigned long long key = valid ? cand[c] : ~0ull;
+        nxt_key = valid ? cand[c] : ~0ull;
+        if (STAGED) {
+            nxt_slot = valid ? cand_slot[c] : 0;
+            nxt.load(stage + (size_t)nxt_slot * g.nchunk, g.nchunk, lit, valid);
+        } else {
+            nxt.load(vecs + (size_t)(valid ? key_id(nxt_key) : 0) * g.nchunk, g.nchunk, lit, valid);
+        }
+    };
+    fetch(0);
+    for (int c0 = 0; c0 < n && K < max_size; c0 += TPW) {
+        const TeamVec<TEAM, CPL> v = nxt;
+        const unsigned long long key = nxt_key;
+        const int slot = nxt_slot;
+        const bool valid = c0 + team < n;
+        if (c0 + TPW < n) fetch(c0 + TPW);  // in flight while this group is tested
         const uint32_t id = key_id(key);
         const float dq = key_dist(key);
-        TeamVec<TEAM, CPL> v;
-        v.load(vecs + (size_t)(valid ? id : 0) * g.nchunk, g.nchunk, lit, valid);
         bool bad = !valid;
-        for (int j = 0; j < K; j++) {
+        auto kept_row = [&](int j) -> const float4* {
+            return STAGED ? stage + (size_t)kept_slot[j] * g.nchunk
+                          : (kvec ? kvec + (size_t)j * g.nchunk
+                                  : vecs + (size_t)key_id(kept_key[j]) * g.nchunk);
+        };
+        int j = 0;
+        for (; j + 4 <= K; j += 4) {  // four kept vectors per iteration: independent fmaf chains
             if (__all_sync(0xffffffffu, bad)) break;
-            const float4* u = kvec ? kvec + (size_t)j * g.nchunk : vecs + (size_t)key_id(kept_key[j]) * g.nchunk;
-            const float duv = v.dist(u, g.nchunk, lit, is_l2);
+            float duv[4];
+            v.dist4(kept_row(j), kept_row(j + 1), kept_row(j + 2), kept_row(j + 3), g.nchunk, lit, is_l2, duv);
+            if (duv[0] < dq || duv[1] < dq || duv[2] < dq || duv[3] < dq) bad = true;
+        }
+        for (; j < K; j++) {
+            if (__all_sync(0xffffffffu, bad)) break;
+            const float duv = v.dist(kept_row(j), g.nchunk, lit, is_l2);
             if (duv < dq) bad = true;
         }
         for (int t = 0; t < TPW; t++) {
             const int bad_t = __shfl_sync(0xffffffffu, (int)bad, t * TEAM);
             if (bad_t) continue;
             if (team == t) {
-                if (lit == 0) kept_key[K] = key;
-                if (kvec) {
+                if (lit == 0) {
+                    kept_key[K] = key;
+                    if (STAGED) kept_slot[K] = slot;
+                }
+                if (!STAGED && kvec) {
 #pragma unroll
                     for (int cc = 0; cc < CPL; cc++) {
                         const int chunk = cc * TEAM + lit;
@@ -101,7 +173,10 @@ __device__ int heuristic(const GraphView& g, const unsigned long long* cand, int
             if (K >= max_size) break;
             if (t + 1 < TPW) {
                 const uint32_t id_t = __shfl_sync(0xffffffffu, id, t * TEAM);
-                const float4* u = kvec ? kvec + (size_t)(K - 1) * g.nchunk : vecs + (size_t)id_t * g.nchunk;
+                const int slot_t = __shfl_sync(0xffffffffu, slot, t * TEAM);
+                const float4* u = STAGED ? stage + (size_t)slot_t * g.nchunk
+                                         : (kvec ? kvec + (size_t)(K - 1) * g.nchunk
+                                                 : vecs + (size_t)id_t * g.nchunk);
                 const float duv = v.dist(u, g.nchunk, lit, is_l2);
                 if (team > t && duv < dq) bad = true;
             }
@@ -125,29 +200,43 @@ __device__ __forceinline__ int row_slot(const GraphView& g, int64_t n_level0, in
 }
 
 struct WarpSmem {
-    unsigned long long* kept_key;  // [kMaxDeg]
-    unsigned long long* cand_a;    // [kMaxDeg + 8]
-    unsigned long long* cand_b;    // [kMaxDeg + 8]
+    unsigned long long* kept_key;  // [deg0]
+    unsigned long long* cand_a;    // [deg0 + 8]
+    unsigned long long* cand_b;    // [deg0 + 8]
+    int32_t* slot_b;               // [deg0 + 8] staging slot of the sorted candidates
+    int32_t* kept_slot;            // [deg0]
+    int32_t* rowid;                // [deg0]
     int32_t* chain;                // [kChainCap]
-    float4* kvec;                  // [deg0][nchunk] or nullptr
+    float4* vbuf;                  // [(deg0 + 1)][nchunk] vector cache (kept / staged candidates) or nullptr
 };
 
-__host__ __device__ inline size_t warp_smem_bytes(int d, int deg0, bool kvec) {
-    return (size_t)kMaxDeg * 8 + 2 * (size_t)(kMaxDeg + 8) * 8 + (size_t)kChainCap * 4 +
-           (kvec ? (size_t)deg0 * d * 4 : 0);
+__host__ __device__ inline size_t warp_smem_bytes(int d, int deg0, bool vbuf) {
+    const size_t c8 = (size_t)(deg0 + 8);
+    size_t b = (size_t)deg0 * 8 + 2 * c8 * 8 + c8 * 4 + 2 * (size_t)deg0 * 4 + (size_t)kChainCap * 4;
+    b = (b + 15) & ~size_t(15);
+    return b + (vbuf ? (size_t)(deg0 + 1) * d * 4 : 0);
 }
 
-__device__ inline WarpSmem carve_warp_smem(unsigned char* p, int d, int deg0, bool kvec) {
+__device__ inline WarpSmem carve_warp_smem(unsigned char* p, int d, int deg0, bool vbuf) {
     WarpSmem w;
+    unsigned char* p0 = p;
+    const size_t c8 = (size_t)(deg0 + 8);
     w.kept_key = reinterpret_cast<unsigned long long*>(p);
-    p += (size_t)kMaxDeg * 8;
+    p += (size_t)deg0 * 8;
     w.cand_a = reinterpret_cast<unsigned long long*>(p);
-    p += (size_t)(kMaxDeg + 8) * 8;
+    p += c8 * 8;
     w.cand_b = reinterpret_cast<unsigned long long*>(p);
-    p += (size_t)(kMaxDeg + 8) * 8;
+    p += c8 * 8;
+    w.slot_b = reinterpret_cast<int32_t*>(p);
+    p += c8 * 4;
+    w.kept_slot = reinterpret_cast<int32_t*>(p);
+    p += (size_t)deg0 * 4;
+    w.rowid = reinterpret_cast<int32_t*>(p);
+    p += (size_t)deg0 * 4;
     w.chain = reinterpret_cast<int32_t*>(p);
     p += (size_t)kChainCap * 4;
-    w.kvec = kvec ? reinterpret_cast<float4*>(p) : nullptr;
+    const size_t used = ((size_t)(p - p0) + 15) & ~size_t(15);
+    w.vbuf = vbuf ? reinterpret_cast<float4*>(p0 + used) : nullptr;
     return w;
 }
 
@@ -172,7 +261,7 @@ __global__ void __launch_bounds__(64) select_and_link_kernel(GraphView g, BuildB
             K = n;
             kept = cand;
         } else {
-            K = heuristic<TEAM, CPL>(g, cand, n, deg, w.kept_key, w.kvec, lane);
+            K = heuristic<TEAM, CPL, false>(g, cand, n, deg, w.kept_key, w.vbuf, nullptr, nullptr, nullptr, lane);
             kept = w.kept_key;
         }
         __syncwarp();
@@ -279,34 +368,97 @@ __global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b,
                 q_loaded = true;
             }
             const int n = deg + 1;
-            if (lane == 0) w.cand_a[0] = pack_key(d_src, (uint32_t)src);
 #pragma unroll
             for (int i = 0; i < kMaxIdsPerLane; i++) {
-                // stage ids so teams can pick them up
                 const int idx = lane + 32 * i;
-                if (idx < deg) w.cand_b[idx] = (unsigned long long)(uint32_t)ids[i];
+                if (idx < deg) w.rowid[idx] = ids[i];
             }
+            if (lane == 0) w.cand_a[0] = pack_key(d_src, (uint32_t)src);
             __syncwarp();
-            for (int r0 = 0; r0 < deg; r0 += TPW) {
-                const int r = r0 + team;
-                const bool valid = r < deg;
-                const uint32_t id = valid ? (uint32_t)w.cand_b[r] : 0u;
-                const float dd = q.dist(vecs + (size_t)id * g.nchunk, g.nchunk, lit, is_l2);
-                if (valid && lit == 0) w.cand_a[1 + r] = pack_key(dd, id);
-            }
-            __syncwarp();
-            // rank sort cand_a[0..n) -> cand_b[0..n)
-            for (int a = lane; a < n; a += 32) {
-                const unsigned long long ka = w.cand_a[a];
-                int rk = 0;
-                for (int j = 0; j < n; j++) {
-                    const unsigned long long kj = w.cand_a[j];
-                    rk += (kj < ka) || (kj == ka && j < a);
+            int K;
+            if (w.vbuf) {
+                // stage all candidate vectors in shared memory (slot r = row member r, slot deg = src),
+                // kGR rows in flight per team, and score them against the row owner on the way
+                constexpr int kGR = 4;
+                for (int r0 = 0; r0 < n; r0 += TPW * kGR) {
+                    float4 x[kGR][CPL];
+                    int rid[kGR];
+#pragma unroll
+                    for (int k2 = 0; k2 < kGR; k2++) {
+                        const int r = r0 + k2 * TPW + team;
+                        rid[k2] = r < deg ? w.rowid[r] : (r == deg ? src : -1);
+                        const float4* rowv = vecs + (size_t)(rid[k2] < 0 ? 0 : rid[k2]) * g.nchunk;
+#pragma unroll
+                        for (int c2 = 0; c2 < CPL; c2++) {
+                            const int chunk = c2 * TEAM + lit;
+                            x[k2][c2] = (rid[k2] >= 0 && chunk < g.nchunk) ? ldg_stream(rowv + chunk)
+                                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+#pragma unroll
+                    for (int k2 = 0; k2 < kGR; k2++) {
+                        const int r = r0 + k2 * TPW + team;
+                        float acc = 0.f;
+#pragma unroll
+                        for (int c2 = 0; c2 < CPL; c2++) {
+                            const int chunk = c2 * TEAM + lit;
+                            if (rid[k2] >= 0 && chunk < g.nchunk) w.vbuf[(size_t)r * g.nchunk + chunk] = x[k2][c2];
+                            if (is_l2) {
+                                float t;
+                                t = x[k2][c2].x - q.x[c2].x; acc = fmaf(t, t, acc);
+                                t = x[k2][c2].y - q.x[c2].y; acc = fmaf(t, t, acc);
+                                t = x[k2][c2].z - q.x[c2].z; acc = fmaf(t, t, acc);
+                                t = x[k2][c2].w - q.x[c2].w; acc = fmaf(t, t, acc);
+                            } else {
+                                acc = fmaf(x[k2][c2].x, q.x[c2].x, acc);
+                                acc = fmaf(x[k2][c2].y, q.x[c2].y, acc);
+                                acc = fmaf(x[k2][c2].z, q.x[c2].z, acc);
+                                acc = fmaf(x[k2][c2].w, q.x[c2].w, acc);
+                            }
+                        }
+#pragma unroll
+                        for (int off = TEAM / 2; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
+                        if (!is_l2) acc = -acc;
+                        if (r < deg && lit == 0) w.cand_a[1 + r] = pack_key(acc, (uint32_t)rid[k2]);
+                    }
                 }
-                w.cand_b[rk] = ka;
+                __syncwarp();
+                // rank sort cand_a[0..n) -> cand_b[0..n) with the staging slot of each entry
+                for (int a = lane; a < n; a += 32) {
+                    const unsigned long long ka = w.cand_a[a];
+                    int rk = 0;
+                    for (int j = 0; j < n; j++) {
+                        const unsigned long long kj = w.cand_a[j];
+                        rk += (kj < ka) || (kj == ka && j < a);
+                    }
+                    w.cand_b[rk] = ka;
+                    w.slot_b[rk] = a == 0 ? deg : a - 1;
+                }
+                __syncwarp();
+                K = heuristic<TEAM, CPL, true>(g, w.cand_b, n, deg, w.kept_key, nullptr, w.vbuf, w.slot_b,
+                                               w.kept_slot, lane);
+            } else {
+                for (int r0 = 0; r0 < deg; r0 += TPW) {
+                    const int r = r0 + team;
+                    const bool valid = r < deg;
+                    const uint32_t id = valid ? (uint32_t)w.rowid[r] : 0u;
+                    const float dd = q.dist(vecs + (size_t)id * g.nchunk, g.nchunk, lit, is_l2);
+                    if (valid && lit == 0) w.cand_a[1 + r] = pack_key(dd, id);
+                }
+                __syncwarp();
+                for (int a = lane; a < n; a += 32) {
+                    const unsigned long long ka = w.cand_a[a];
+                    int rk = 0;
+                    for (int j = 0; j < n; j++) {
+                        const unsigned long long kj = w.cand_a[j];
+                        rk += (kj < ka) || (kj == ka && j < a);
+                    }
+                    w.cand_b[rk] = ka;
+                }
+                __syncwarp();
+                K = heuristic<TEAM, CPL, false>(g, w.cand_b, n, deg, w.kept_key, nullptr, nullptr, nullptr,
+                                                nullptr, lane);
             }
-            __syncwarp();
-            const int K = heuristic<TEAM, CPL>(g, w.cand_b, n, deg, w.kept_key, w.kvec, lane);
             __syncwarp();
             for (int i = lane; i < deg; i += 32) row[i] = i < K ? (int)key_id(w.kept_key[K - 1 - i]) : -1;
             __syncwarp();
@@ -317,7 +469,7 @@ __global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b,
 template <int TEAM, int CPL>
 cudaError_t launch_build_pair(bool backlinks, const GraphView& g, const BuildBatch& b, int num_sms,
                               cudaStream_t stream) {
-    const bool kvec = (size_t)g.deg0 * g.d * 4 <= 48 * 1024;
+    const bool kvec = (size_t)(g.deg0 + 1) * g.d * 4 <= 48 * 1024;
     const int wpb = 2;
     const size_t smem = wpb * warp_smem_bytes(g.d, g.deg0, kvec);
     auto ks = select_and_link_kernel<TEAM, CPL>;

@@ -159,8 +159,9 @@ struct bh_index {
     int auto_hash_bits(int ef, int req) const {
         const int lo = min_hash_bits(ef);
         if (req > 0) return std::min(std::max(req, lo), 16);
-        int b = ceil_log2((long long)ef * 8);
-        b = std::max(b, 10);
+        // measured on 1M x 128 (profiles/README.md): ~4 slots per list entry is the sweet spot
+        int b = ceil_log2((long long)ef * 4);
+        b = std::max(b, 9);
         return std::min(std::max(b, lo), 15);
     }
     int auto_warps(int ef, int hash_bits, int req) const {
@@ -172,9 +173,12 @@ struct bh_index {
         if (2 * s <= smem_optin) return 2;
         return 4;
     }
-    static int beam_variant() {
+    // Register/occupancy variant of the one-warp-per-query kernel (beam_kernel.cu): 1 = 80 regs,
+    // 6 CTAs/SM, used while 24 queries' state fits in one SM's shared memory; else 0 = 128 regs, 4 CTAs.
+    int beam_variant(int ef, int hash_bits) const {
         const char* e = getenv("BH_BEAM_VARIANT");
-        return e ? atoi(e) : 0;
+        if (e) return atoi(e);
+        return 24 * bh::beam_group_smem(d, ef, hash_bits) <= smem_optin - 6 * 1024 ? 1 : 0;
     }
 
     int ensure_capacity(int64_t n_new_total, int64_t upper_rows_total) {
@@ -237,7 +241,7 @@ int search_device_impl(const bh_index* h, int64_t n, const float* xq_d, int64_t 
     t.stats = stats_d;
     t.counter = h->counter.p;
     BH_CUDA(cudaMemsetAsync(h->counter.p, 0, sizeof(int), h->stream));
-    BH_CUDA(bh::launch_beam(h->view(), t, W, bh_index::beam_variant(), h->num_sms, h->stream, nullptr));
+    BH_CUDA(bh::launch_beam(h->view(), t, W, h->beam_variant(ef, hb), h->num_sms, h->stream, nullptr));
     bh::count_launch();
     return 0;
 }
@@ -423,7 +427,7 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
             t.stats = nullptr;
             t.counter = h->counter.p;
             BH_CUDA(cudaMemsetAsync(h->counter.p, 0, sizeof(int), h->stream));
-            BH_CUDA(bh::launch_beam(g, t, W, bh_index::beam_variant(), h->num_sms, h->stream, nullptr));
+            BH_CUDA(bh::launch_beam(g, t, W, h->beam_variant(efc, hb), h->num_sms, h->stream, nullptr));
             bh::BuildBatch b{};
             b.items = t.items;
             b.cand_lists = h->cand_lists.p;

@@ -21,7 +21,7 @@ ap.add_argument("--d1", type=int, default=32)
 ap.add_argument("--M", type=int, default=32)
 ap.add_argument("--efc", type=int, default=200)
 ap.add_argument("--nq", type=int, default=10000)
-ap.add_argument("--divisors", type=str, default="16")
+ap.add_argument("--divisors", type=str, default="0")
 ap.add_argument("--max_batch", type=str, default="8192")
 ap.add_argument("--efs", type=str, default="16,32,64,128,256,512")
 ap.add_argument("--Ws", type=str, default="0")
@@ -31,7 +31,7 @@ ap.add_argument("--build_hb", type=int, default=0)
 ap.add_argument("--cpu", type=int, default=0, help="also build with the CPU oracle using this many threads")
 ap.add_argument("--ip", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--variants", type=str, default="0")
+ap.add_argument("--variants", type=str, default="auto")
 a = ap.parse_args()
 
 metric = 0 if a.ip else 1
@@ -77,7 +77,10 @@ for div in [int(x) for x in a.divisors.split(",")]:
         for ef in [int(e) for e in a.efs.split(",")]:
             for W in [int(x) for x in a.Ws.split(",")]:
                 for hb, var in [(int(x), v) for x in a.hbs.split(",") for v in a.variants.split(",")]:
-                    os.environ["BH_BEAM_VARIANT"] = var
+                    if var == "auto":
+                        os.environ.pop("BH_BEAM_VARIANT", None)
+                    else:
+                        os.environ["BH_BEAM_VARIANT"] = var
                     try:
                         D, I, S = idx.search(xq, 10, efSearch=ef, stats=True, warps_per_query=W, hash_bits=hb)
                     except RuntimeError as e:
