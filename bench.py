@@ -125,9 +125,16 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
-def make_data(a, seed):
+QUERY_POOL = 8  # query sets generated (one per possible rank); fixed so the database is the same for every N
+
+
+def make_data(a, rank=0):
+    """Database + this rank's query set. The pool of QUERY_POOL x nq queries and the database come
+    from ONE seeded draw, so xb is bit-identical for every N and every rank; rank r takes slice r."""
     from hnsw_b200.datasets import synthetic_dataset
-    return synthetic_dataset(a.d, a.n, a.nq, d1=a.d1, seed=seed)
+    xb, xq_all = synthetic_dataset(a.d, a.n, QUERY_POOL * a.nq, d1=a.d1, seed=1338)
+    r = rank % QUERY_POOL
+    return xb, np.ascontiguousarray(xq_all[r * a.nq:(r + 1) * a.nq])
 
 
 def native_oracle():
@@ -148,7 +155,7 @@ def run_reference(a):
         return
     om, path = native_oracle()
     threads = os.cpu_count() or 1
-    xb, xq = make_data(a, 1338)
+    xb, xq = make_data(a, 0)
     # bounded build: calibrate on 50k vectors, keep the whole build under ~120 s
     o = om.OracleHNSWFlat(a.d, a.M, om.METRIC_L2, lib_path=path)
     o.efConstruction = a.efc
@@ -237,8 +244,8 @@ def run_b200(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- data: every rank indexes its own 1M-vector set (rank-specific seed) + its own queries
-    xb, xq = make_data(a, 1338 + rank)
+    # ---- data: every rank indexes the SAME database (replicas) and answers its own query set
+    xb, xq = make_data(a, rank)
     xb_t, xq_t = torch.from_numpy(xb).to(dev), torch.from_numpy(xq).to(dev)
     _, gt_t = exact_knn_torch(xb_t, xq_t, a.k)
     gt = gt_t.cpu().numpy()
@@ -277,9 +284,9 @@ def run_b200(a):
             ef_sel = ef
     if ef_sel is None:
         ef_sel = EF_GRID[-1]
-    if world > 1:  # all ranks time the same efSearch
+    if world > 1:  # every rank times rank 0's efSearch (= the N=1 workload's operating point)
         t = torch.tensor([ef_sel], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.broadcast(t, src=0)
         ef_sel = int(t.item())
     sel = next(x for x in sweep if x["efSearch"] == ef_sel)
 
@@ -308,6 +315,7 @@ def run_b200(a):
     ms_step = ms_total / a.steps
     value = world * a.nq / (ms_step * 1e-3)
     rec_timed = recall_at_k(I_d.cpu().numpy(), gt)
+    rec_min = -max_over_ranks(-rec_timed)
 
     # ---- timed region 2: `e2e` — the public call with pinned HOST buffers, copies inside
     xq_pin = torch.empty(a.nq, a.d, dtype=torch.float32).pin_memory()
@@ -325,26 +333,37 @@ def run_b200(a):
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e = world * a.nq * a.steps / t_e2e
 
-    # ---- north-star sharded path (N > 1): broadcast queries, all-gather top-k, merge kernel
+    # ---- north-star sharded path (N > 1): the same database split into N contiguous shards, one
+    #      sub-graph per GPU; queries broadcast, all-gather of per-shard top-k, warp merge kernel
     sharded = None
     if world > 1 and not a.no_sharded:
+        n_sh = a.n // world
+        lo = rank * n_sh
+        shard = hnsw_b200.IndexHNSWFlat(a.d, a.M, hnsw_b200.METRIC_L2, device=local)
+        shard.hnsw.efConstruction = a.efc
+        shard.add(xb[lo:lo + n_sh])
+        sstream = torch.cuda.ExternalStream(shard.stream_ptr, device=dev)
         q_b = xq_t.clone()
         dist.broadcast(q_b, src=0)
+        gt0 = torch.from_numpy(gt).to(dev)
+        dist.broadcast(gt0, src=0)
+        Dl = torch.empty(a.nq, a.k, device=dev)
+        Il = torch.empty(a.nq, a.k, dtype=torch.int64, device=dev)
         Dg = torch.empty(world, a.nq, a.k, device=dev)
         Ig = torch.empty(world, a.nq, a.k, dtype=torch.int64, device=dev)
         Dm = torch.empty(a.nq, a.k, device=dev)
         Im = torch.empty(a.nq, a.k, dtype=torch.int64, device=dev)
-        offs = np.arange(world, dtype=np.int64) * a.n
+        offs = np.arange(world, dtype=np.int64) * n_sh
         cur = torch.cuda.current_stream(dev)
 
         def step_sharded():
-            idx.search_device(q_b.data_ptr(), a.nq, a.k, D_d.data_ptr(), I_d.data_ptr(), efSearch=ef_sel)
-            cur.wait_stream(stream)
-            dist.all_gather_into_tensor(Dg, D_d)
-            dist.all_gather_into_tensor(Ig, I_d)
+            sstream.wait_stream(cur)
+            shard.search_device(q_b.data_ptr(), a.nq, a.k, Dl.data_ptr(), Il.data_ptr(), efSearch=ef_sel)
+            cur.wait_stream(sstream)
+            dist.all_gather_into_tensor(Dg, Dl)
+            dist.all_gather_into_tensor(Ig, Il)
             hnsw_b200.merge_topk_device(Dg.data_ptr(), Ig.data_ptr(), world, a.nq, a.k, hnsw_b200.METRIC_L2,
                                         offs, Dm.data_ptr(), Im.data_ptr(), cur.cuda_stream)
-            stream.wait_stream(cur)
 
         for _ in range(3):
             step_sharded()
@@ -356,21 +375,13 @@ def run_b200(a):
         e1.record(cur)
         barrier()
         ms_sh = max_over_ranks(e0.elapsed_time(e1)) / a.steps
-        # recall of the merged result against the exact top-k over the union of all shards
-        _, gts = exact_knn_torch(xb_t, q_b, a.k)
-        dts = ((q_b[:, None, :] - xb_t[gts]) ** 2).sum(-1)
-        Dall = torch.empty(world, a.nq, a.k, device=dev)
-        Iall = torch.empty(world, a.nq, a.k, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(Dall, dts.contiguous())
-        dist.all_gather_into_tensor(Iall, (gts + rank * a.n).contiguous())
-        dcat = Dall.permute(1, 0, 2).reshape(a.nq, -1)
-        icat = Iall.permute(1, 0, 2).reshape(a.nq, -1)
-        selg = torch.topk(dcat, a.k, dim=1, largest=False).indices
-        gt_glob = torch.gather(icat, 1, selg).cpu().numpy()
         sharded = {"value": round(a.nq / (ms_sh * 1e-3), 1), "unit": "queries/s", "ms_per_step": round(ms_sh, 3),
-                   "db_vectors": world * a.n, "recall_at_10": round(recall_at_k(Im.cpu().numpy(), gt_glob), 4),
-                   "allgather_bytes_per_rank": a.nq * a.k * 12,
-                   "note": "every query searches all N shards; QPS is per global database, not per GPU"}
+                   "db_vectors": n_sh * world, "shard_vectors": n_sh,
+                   "recall_at_10": round(recall_at_k(Im.cpu().numpy(), gt0.cpu().numpy()), 4),
+                   "allgather_bytes_per_rank": a.nq * a.k * 12, "efSearch": ef_sel,
+                   "note": "same database split over N GPUs; every query visits every shard, so this buys "
+                           "capacity/latency, not QPS"}
+        del shard
 
     # ---- CPU baseline (rank 0, N=1): oracle port searching the SAME graph on the host cores
     cpu_baseline = None
@@ -421,7 +432,8 @@ def run_b200(a):
             "config": {"workload": f"SIFT1M-shape {a.n}x{a.d} fp32 L2, M={a.M} efC={a.efc}, {a.nq}-query batch, "
                                    f"k={a.k}" + ("" if world == 1 else f"; {world} replicas, each GPU its own "
                                                                         f"{a.n}-vector index and {a.nq} queries"),
-                       "efSearch": ef_sel, "recall_at_10": round(rec_timed, 4), "d1": a.d1, "seed": 1338,
+                       "efSearch": ef_sel, "recall_at_10": round(rec_timed, 4),
+                       "recall_at_10_min_over_ranks": round(rec_min, 4), "d1": a.d1, "seed": 1338,
                        "l2_policy": "no flush: index 768 MB and ~%d MB touched per step exceed the 126 MB L2"
                                     % round(sel["bytes_per_query"] * a.nq / 1e6)},
             "build_vectors_per_s": round(a.n / t_build, 1),

@@ -53,6 +53,28 @@ struct TeamVec {
         for (int off = TEAM / 2; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
         return is_l2 ? acc : -acc;
     }
+    // Distance to a vector held in another lane-sliced register array (same arithmetic).
+    __device__ __forceinline__ float dist(const float4 (&o)[CPL], int nchunk, int lit, bool is_l2, bool) const {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+            if (is_l2) {
+                float t;
+                t = o[c].x - x[c].x; acc = fmaf(t, t, acc);
+                t = o[c].y - x[c].y; acc = fmaf(t, t, acc);
+                t = o[c].z - x[c].z; acc = fmaf(t, t, acc);
+                t = o[c].w - x[c].w; acc = fmaf(t, t, acc);
+            } else {
+                acc = fmaf(o[c].x, x[c].x, acc);
+                acc = fmaf(o[c].y, x[c].y, acc);
+                acc = fmaf(o[c].z, x[c].z, acc);
+                acc = fmaf(o[c].w, x[c].w, acc);
+            }
+        }
+#pragma unroll
+        for (int off = TEAM / 2; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
+        return is_l2 ? acc : -acc;
+    }
     // Four independent pairs at once (same per-pair arithmetic; the four fmaf chains interleave).
     __device__ __forceinline__ void dist4(const float4* r0, const float4* r1, const float4* r2,
                                           const float4* r3, int nchunk, int lit, bool is_l2,
@@ -195,6 +217,10 @@ __device__ __forceinline__ int32_t* row_ptr_rw(const GraphView& g, int v, int le
     return g.upper_nbr + ((size_t)b + (level - 1)) * g.degU;
 }
 
+__device__ __forceinline__ uint8_t* nver_ptr(const GraphView& g, const BuildBatch& b, int v, int level) {
+    return level == 0 ? b.nver0 + v : b.nverU + (__ldg(g.upper_base + v) + (level - 1));
+}
+
 __device__ __forceinline__ int row_slot(const GraphView& g, int64_t n_level0, int v, int level) {
     return level == 0 ? v : (int)(n_level0 + __ldg(g.upper_base + v) + (level - 1));
 }
@@ -208,16 +234,22 @@ struct WarpSmem {
     int32_t* rowid;                // [deg0]
     int32_t* chain;                // [kChainCap]
     float4* vbuf;                  // [(deg0 + 1)][nchunk] vector cache (kept / staged candidates) or nullptr
+    float* dsx;                    // [max_special][deg0 + 8] d(special_i, candidate_a)   (backlink only)
+    float4* spec_vec;              // [max_special][nchunk] vectors of the special candidates (backlink only)
 };
 
-__host__ __device__ inline size_t warp_smem_bytes(int d, int deg0, bool vbuf) {
+__host__ __device__ inline size_t warp_smem_bytes(int d, int deg0, bool vbuf, int max_special = 0) {
     const size_t c8 = (size_t)(deg0 + 8);
     size_t b = (size_t)deg0 * 8 + 2 * c8 * 8 + c8 * 4 + 2 * (size_t)deg0 * 4 + (size_t)kChainCap * 4;
     b = (b + 15) & ~size_t(15);
-    return b + (vbuf ? (size_t)(deg0 + 1) * d * 4 : 0);
+    b += (vbuf ? (size_t)(deg0 + 1) * d * 4 : 0);
+    b += (size_t)max_special * c8 * 4;
+    b = (b + 15) & ~size_t(15);
+    b += (size_t)max_special * d * 4;
+    return b;
 }
 
-__device__ inline WarpSmem carve_warp_smem(unsigned char* p, int d, int deg0, bool vbuf) {
+__device__ inline WarpSmem carve_warp_smem(unsigned char* p, int d, int deg0, bool vbuf, int max_special = 0) {
     WarpSmem w;
     unsigned char* p0 = p;
     const size_t c8 = (size_t)(deg0 + 8);
@@ -235,8 +267,13 @@ __device__ inline WarpSmem carve_warp_smem(unsigned char* p, int d, int deg0, bo
     p += (size_t)deg0 * 4;
     w.chain = reinterpret_cast<int32_t*>(p);
     p += (size_t)kChainCap * 4;
-    const size_t used = ((size_t)(p - p0) + 15) & ~size_t(15);
+    size_t used = ((size_t)(p - p0) + 15) & ~size_t(15);
     w.vbuf = vbuf ? reinterpret_cast<float4*>(p0 + used) : nullptr;
+    used += vbuf ? (size_t)(deg0 + 1) * d * 4 : 0;
+    w.dsx = reinterpret_cast<float*>(p0 + used);
+    used += (size_t)max_special * c8 * 4;
+    used = (used + 15) & ~size_t(15);
+    w.spec_vec = reinterpret_cast<float4*>(p0 + used);
     return w;
 }
 
@@ -257,14 +294,17 @@ __global__ void __launch_bounds__(64) select_and_link_kernel(GraphView g, BuildB
         const int n = b.cand_counts[item];
         int K;
         const unsigned long long* kept;
+        bool verified = false;
         if (n < deg) {  // shrink_neighbor_list returns early: keep everything
             K = n;
             kept = cand;
         } else {
+            verified = true;
             K = heuristic<TEAM, CPL, false>(g, cand, n, deg, w.kept_key, w.vbuf, nullptr, nullptr, nullptr, lane);
             kept = w.kept_key;
         }
         __syncwarp();
+        if (lane == 0) *nver_ptr(g, b, pt, level) = verified ? (uint8_t)K : (uint8_t)0;
         // faiss pops link_targets farthest-first: row[i] = kept[K-1-i]
         for (int i = lane; i < g.deg0; i += 32) {
             const int e = item * g.deg0 + i;
@@ -289,27 +329,42 @@ __global__ void __launch_bounds__(64) select_and_link_kernel(GraphView g, BuildB
 }
 
 // ---- App. A.11 add_link(dst ← src) for every staged back-edge ------------------------
+//
+// Full rows re-run shrink_neighbor_list on the 2M+1 candidates. Done naively that is ~2000
+// pairwise distances per back-link (what faiss does). Here each row carries a *verified prefix*
+// `nver`: members at positions [0, nver) came out of one heuristic run, so every pair u ≺ v among
+// them already satisfies d(u,v) >= d(v,owner) — a static fact about those vectors. Re-running the
+// heuristic on (row ∪ {src}) can therefore only be decided by pairs that involve a *special*
+// candidate: src itself or a member appended since the last shrink. The incremental path streams
+// the 2M+1 vectors once, scoring each against the owner and against the (few) specials, and then
+// replays the heuristic on that small table — the same comparisons on the same values as the full
+// run, hence the identical result, at ~1/10 of the arithmetic and no large shared-memory stage.
 template <int TEAM, int CPL>
 __global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b, int use_kvec) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int TPW = 32 / TEAM;
+    constexpr int kGR = 4;  // candidate rows in flight per team
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int lit = lane % TEAM, team = lane / TEAM;
-    const WarpSmem w = carve_warp_smem(smem_raw + wib * warp_smem_bytes(g.d, g.deg0, use_kvec), g.d,
-                                       g.deg0, use_kvec);
+    const WarpSmem w = carve_warp_smem(smem_raw + wib * warp_smem_bytes(g.d, g.deg0, false, b.max_special),
+                                       g.d, g.deg0, false, b.max_special);
     const float4* __restrict__ vecs = reinterpret_cast<const float4*>(g.vecs);
     const bool is_l2 = g.is_l2 != 0;
+    const int stride = g.deg0 + 8;
+    int32_t* kspec = w.chain + kChainCap - 32;  // last 32 ints of the chain buffer: kept specials
+    const int chain_cap = kChainCap - 32;
     const int nwarps = gridDim.x * (blockDim.x >> 5);
     const int n_edges = b.n_items * g.deg0;
+    (void)use_kvec;
     for (int e0 = blockIdx.x * (blockDim.x >> 5) + wib; e0 < n_edges; e0 += nwarps) {
         const int slot = b.edge_dst_slot[e0];
         if (slot < 0 || b.edge_next[e0] != -1) continue;  // only the tail of a row's list owns it
-        // collect the row's pending edges (pushed in arbitrary order) and sort by edge index
+        // collect the row's pending edges (pushed in arbitrary order); applied in edge-index order
         int c = 0, head = -1;
         if (lane == 0) {
             head = b.slot_head[slot];
             for (int e = head; e >= 0; e = b.edge_next[e]) {
-                if (c < kChainCap) w.chain[c] = e;
+                if (c < chain_cap) w.chain[c] = e;
                 c++;
             }
             b.slot_head[slot] = -1;
@@ -317,11 +372,14 @@ __global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b,
         c = __shfl_sync(0xffffffffu, c, 0);
         head = __shfl_sync(0xffffffffu, head, 0);
         __syncwarp();
-        const bool overflow = c > kChainCap;
+        const bool overflow = c > chain_cap;
         int last_done = -1;
         const int dst = b.edge_dst[e0], level = b.edge_level[e0];
         int deg;
         int32_t* row = row_ptr_rw(g, dst, level, deg);
+        uint8_t* nvp = nver_ptr(g, b, dst, level);
+        int nv = *nvp;
+        const int nv0 = nv;
         TeamVec<TEAM, CPL> q;  // the destination vertex's own vector (base of the distances)
         bool q_loaded = false;
 
@@ -333,7 +391,7 @@ __global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b,
                     const int v = w.chain[i];
                     if (v > last_done && v < e) e = v;
                 }
-            } else if (lane == 0) {  // rare (> kChainCap edges to one row): re-walk the list
+            } else if (lane == 0) {  // rare (more pending edges than the buffer holds): re-walk the list
                 for (int x = head; x >= 0; x = b.edge_next[x])
                     if (x > last_done && x < e) e = x;
             }
@@ -362,7 +420,8 @@ __global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b,
                 __syncwarp();
                 continue;
             }
-            // full row: the deg+1 candidates fight it out (shrink_neighbor_list)
+            // full row: the deg+1 candidates fight it out (shrink_neighbor_list).
+            // candidate index a: 0 = src, 1 + p = row member at position p
             if (!q_loaded) {
                 q.load(vecs + (size_t)dst * g.nchunk, g.nchunk, lit, true);
                 q_loaded = true;
@@ -373,109 +432,116 @@ __global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b,
                 const int idx = lane + 32 * i;
                 if (idx < deg) w.rowid[idx] = ids[i];
             }
-            if (lane == 0) w.cand_a[0] = pack_key(d_src, (uint32_t)src);
+            if (nv > deg) nv = deg;
+            const int ns = 1 + (deg - nv);  // specials: src + members appended since the last shrink
+            const bool incremental = ns <= b.max_special;
             __syncwarp();
-            int K;
-            if (w.vbuf) {
-                // stage all candidate vectors in shared memory (slot r = row member r, slot deg = src),
-                // kGR rows in flight per team, and score them against the row owner on the way
-                constexpr int kGR = 4;
-                for (int r0 = 0; r0 < n; r0 += TPW * kGR) {
-                    float4 x[kGR][CPL];
-                    int rid[kGR];
-#pragma unroll
-                    for (int k2 = 0; k2 < kGR; k2++) {
-                        const int r = r0 + k2 * TPW + team;
-                        rid[k2] = r < deg ? w.rowid[r] : (r == deg ? src : -1);
-                        const float4* rowv = vecs + (size_t)(rid[k2] < 0 ? 0 : rid[k2]) * g.nchunk;
+            if (incremental) {  // specials' vectors -> shared memory
+                for (int s0 = 0; s0 < ns; s0 += TPW) {
+                    const int si = s0 + team;
+                    if (si < ns) {
+                        const int id = si == 0 ? src : w.rowid[nv + si - 1];
+                        TeamVec<TEAM, CPL> tv;
+                        tv.load(vecs + (size_t)id * g.nchunk, g.nchunk, lit, true);
 #pragma unroll
                         for (int c2 = 0; c2 < CPL; c2++) {
                             const int chunk = c2 * TEAM + lit;
-                            x[k2][c2] = (rid[k2] >= 0 && chunk < g.nchunk) ? ldg_stream(rowv + chunk)
-                                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (chunk < g.nchunk) w.spec_vec[(size_t)si * g.nchunk + chunk] = tv.x[c2];
                         }
-                    }
-#pragma unroll
-                    for (int k2 = 0; k2 < kGR; k2++) {
-                        const int r = r0 + k2 * TPW + team;
-                        float acc = 0.f;
-#pragma unroll
-                        for (int c2 = 0; c2 < CPL; c2++) {
-                            const int chunk = c2 * TEAM + lit;
-                            if (rid[k2] >= 0 && chunk < g.nchunk) w.vbuf[(size_t)r * g.nchunk + chunk] = x[k2][c2];
-                            if (is_l2) {
-                                float t;
-                                t = x[k2][c2].x - q.x[c2].x; acc = fmaf(t, t, acc);
-                                t = x[k2][c2].y - q.x[c2].y; acc = fmaf(t, t, acc);
-                                t = x[k2][c2].z - q.x[c2].z; acc = fmaf(t, t, acc);
-                                t = x[k2][c2].w - q.x[c2].w; acc = fmaf(t, t, acc);
-                            } else {
-                                acc = fmaf(x[k2][c2].x, q.x[c2].x, acc);
-                                acc = fmaf(x[k2][c2].y, q.x[c2].y, acc);
-                                acc = fmaf(x[k2][c2].z, q.x[c2].z, acc);
-                                acc = fmaf(x[k2][c2].w, q.x[c2].w, acc);
-                            }
-                        }
-#pragma unroll
-                        for (int off = TEAM / 2; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
-                        if (!is_l2) acc = -acc;
-                        if (r < deg && lit == 0) w.cand_a[1 + r] = pack_key(acc, (uint32_t)rid[k2]);
                     }
                 }
                 __syncwarp();
-                // rank sort cand_a[0..n) -> cand_b[0..n) with the staging slot of each entry
-                for (int a = lane; a < n; a += 32) {
-                    const unsigned long long ka = w.cand_a[a];
-                    int rk = 0;
-                    for (int j = 0; j < n; j++) {
-                        const unsigned long long kj = w.cand_a[j];
-                        rk += (kj < ka) || (kj == ka && j < a);
+            }
+            // stream every candidate once: distance to the owner (+ to each special)
+            for (int r0 = 0; r0 < n; r0 += TPW * kGR) {
+                TeamVec<TEAM, CPL> x[kGR];
+                int cid[kGR];
+#pragma unroll
+                for (int k2 = 0; k2 < kGR; k2++) {
+                    const int a = r0 + k2 * TPW + team;
+                    cid[k2] = a >= n ? -1 : (a == 0 ? src : w.rowid[a - 1]);
+                    const float4* rowv = vecs + (size_t)(cid[k2] < 0 ? 0 : cid[k2]) * g.nchunk;
+#pragma unroll
+                    for (int c2 = 0; c2 < CPL; c2++) {
+                        const int chunk = c2 * TEAM + lit;
+                        x[k2].x[c2] = (cid[k2] >= 0 && chunk < g.nchunk) ? ldg_stream(rowv + chunk)
+                                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    w.cand_b[rk] = ka;
-                    w.slot_b[rk] = a == 0 ? deg : a - 1;
                 }
-                __syncwarp();
-                K = heuristic<TEAM, CPL, true>(g, w.cand_b, n, deg, w.kept_key, nullptr, w.vbuf, w.slot_b,
-                                               w.kept_slot, lane);
+#pragma unroll
+                for (int k2 = 0; k2 < kGR; k2++) {
+                    const int a = r0 + k2 * TPW + team;
+                    const float dd = x[k2].dist(q.x, g.nchunk, lit, is_l2, true);
+                    if (cid[k2] >= 0 && lit == 0)
+                        w.cand_a[a] = a == 0 ? pack_key(d_src, (uint32_t)src) : pack_key(dd, (uint32_t)cid[k2]);
+                    if (incremental) {
+                        for (int si = 0; si < ns; si++) {
+                            const float ds = x[k2].dist(w.spec_vec + (size_t)si * g.nchunk, g.nchunk, lit, is_l2);
+                            if (cid[k2] >= 0 && lit == 0) w.dsx[si * stride + a] = ds;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            // rank sort cand_a[0..n) -> cand_b[0..n), remembering each entry's candidate index
+            for (int a = lane; a < n; a += 32) {
+                const unsigned long long ka = w.cand_a[a];
+                int rk = 0;
+                for (int j = 0; j < n; j++) {
+                    const unsigned long long kj = w.cand_a[j];
+                    rk += (kj < ka) || (kj == ka && j < a);
+                }
+                w.cand_b[rk] = ka;
+                w.slot_b[rk] = a;
+            }
+            __syncwarp();
+            int K = 0;
+            if (incremental) {
+                int nks = 0;  // kept specials so far
+                for (int cpos = 0; cpos < n; cpos++) {
+                    const unsigned long long key = w.cand_b[cpos];
+                    const int a = w.slot_b[cpos];
+                    const float dq = key_dist(key);
+                    const int si = a == 0 ? 0 : ((a - 1) >= nv ? 1 + (a - 1 - nv) : -1);
+                    bool bad = false;
+                    if (si < 0) {  // verified member: only a kept special can prune it
+                        if (lane < nks) bad = w.dsx[kspec[lane] * stride + a] < dq;
+                    } else {       // special: any kept candidate can prune it
+                        for (int j = lane; j < K; j += 32) bad |= w.dsx[si * stride + w.kept_slot[j]] < dq;
+                    }
+                    if (__any_sync(0xffffffffu, bad)) continue;
+                    if (lane == 0) {
+                        w.kept_key[K] = key;
+                        w.kept_slot[K] = a;
+                        if (si >= 0) kspec[nks] = si;
+                    }
+                    K++;
+                    nks += si >= 0;
+                    __syncwarp();
+                    if (K >= deg) break;
+                }
             } else {
-                for (int r0 = 0; r0 < deg; r0 += TPW) {
-                    const int r = r0 + team;
-                    const bool valid = r < deg;
-                    const uint32_t id = valid ? (uint32_t)w.rowid[r] : 0u;
-                    const float dd = q.dist(vecs + (size_t)id * g.nchunk, g.nchunk, lit, is_l2);
-                    if (valid && lit == 0) w.cand_a[1 + r] = pack_key(dd, id);
-                }
-                __syncwarp();
-                for (int a = lane; a < n; a += 32) {
-                    const unsigned long long ka = w.cand_a[a];
-                    int rk = 0;
-                    for (int j = 0; j < n; j++) {
-                        const unsigned long long kj = w.cand_a[j];
-                        rk += (kj < ka) || (kj == ka && j < a);
-                    }
-                    w.cand_b[rk] = ka;
-                }
-                __syncwarp();
                 K = heuristic<TEAM, CPL, false>(g, w.cand_b, n, deg, w.kept_key, nullptr, nullptr, nullptr,
                                                 nullptr, lane);
             }
             __syncwarp();
             for (int i = lane; i < deg; i += 32) row[i] = i < K ? (int)key_id(w.kept_key[K - 1 - i]) : -1;
+            nv = K;  // the whole row is now one heuristic output
             __syncwarp();
         }
+        if (lane == 0 && nv != nv0) *nvp = (uint8_t)nv;
     }
 }
 
 template <int TEAM, int CPL>
 cudaError_t launch_build_pair(bool backlinks, const GraphView& g, const BuildBatch& b, int num_sms,
                               cudaStream_t stream) {
-    const bool kvec = (size_t)(g.deg0 + 1) * g.d * 4 <= 48 * 1024;
     const int wpb = 2;
-    const size_t smem = wpb * warp_smem_bytes(g.d, g.deg0, kvec);
-    auto ks = select_and_link_kernel<TEAM, CPL>;
-    auto kb = backlink_kernel<TEAM, CPL>;
     cudaError_t e;
     if (!backlinks) {
+        const bool kvec = (size_t)(g.deg0 + 1) * g.d * 4 <= 48 * 1024;
+        const size_t smem = wpb * warp_smem_bytes(g.d, g.deg0, kvec);
+        auto ks = select_and_link_kernel<TEAM, CPL>;
         e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int occ = 1;
@@ -486,6 +552,8 @@ cudaError_t launch_build_pair(bool backlinks, const GraphView& g, const BuildBat
         if (grid < 1) grid = 1;
         ks<<<(unsigned)grid, 32 * wpb, smem, stream>>>(g, b, (int)kvec);
     } else {
+        const size_t smem = wpb * warp_smem_bytes(g.d, g.deg0, false, b.max_special);
+        auto kb = backlink_kernel<TEAM, CPL>;
         e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int occ = 1;
@@ -494,7 +562,7 @@ cudaError_t launch_build_pair(bool backlinks, const GraphView& g, const BuildBat
         const long long need = ((long long)b.n_items * g.deg0 + wpb - 1) / wpb;
         if (grid > need) grid = need;
         if (grid < 1) grid = 1;
-        kb<<<(unsigned)grid, 32 * wpb, smem, stream>>>(g, b, (int)kvec);
+        kb<<<(unsigned)grid, 32 * wpb, smem, stream>>>(g, b, 0);
     }
     return cudaGetLastError();
 }

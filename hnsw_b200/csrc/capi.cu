@@ -6,6 +6,7 @@
 // There is no CPU fallback anywhere in this file: every path ends in a kernel launch.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -92,6 +93,7 @@ struct bh_index {
 
     DevBuf<float> vecs;
     DevBuf<int32_t> nbr0, upper_base_d, upper_nbr, slot_head;
+    DevBuf<uint8_t> nver0, nverU;  // verified prefix per adjacency row (build_kernels.cu)
     int64_t slot_level0 = 0;  // slot numbering base used when slot_head was laid out
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -188,10 +190,12 @@ struct bh_index {
             BH_CUDA(vecs.reserve((size_t)cap * d, stream, true, (size_t)old_n * d));
             BH_CUDA(nbr0.reserve((size_t)cap * deg0(), stream, true, (size_t)old_n * deg0()));
             BH_CUDA(upper_base_d.reserve((size_t)cap, stream, true, (size_t)old_n));
+            BH_CUDA(nver0.reserve((size_t)cap, stream, true, (size_t)old_n));
         }
         if ((size_t)upper_rows_total * M > upper_nbr.cap) {
             size_t cap = std::max<size_t>((size_t)upper_rows_total * M, upper_nbr.cap * 3 / 2);
             BH_CUDA(upper_nbr.reserve(cap, stream, true, (size_t)n_upper_rows * M));
+            BH_CUDA(nverU.reserve(cap / M + 1, stream, true, (size_t)n_upper_rows));
         }
         // pending-list heads: one per adjacency row, all -1 between batches
         const int64_t level0_rows = (int64_t)(vecs.cap / d);
@@ -205,6 +209,7 @@ struct bh_index {
     }
 
     void free_all() {
+        nver0.release(); nverU.release();
         vecs.release(); nbr0.release(); upper_base_d.release(); upper_nbr.release(); slot_head.release();
         counter.release(); q_d.release(); D_d.release(); I_d.release(); stats_d.release();
         items_d.release(); cand_lists.release(); cand_counts.release();
@@ -284,6 +289,15 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     BH_CUDA(cudaSetDevice(h->device));
     const int64_t n0 = h->ntotal;
     const int d = h->d, M = h->M, deg0 = h->deg0();
+    const bool dbg = getenv("BH_DEBUG_TIMING") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!dbg) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bh add] %-28s %8.2f ms\n", what,
+                std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
 
     // -- prepare_level_tab (App. A.2): levels, row allocation
     std::vector<int32_t> new_levels(n);
@@ -307,7 +321,9 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
         }
     }
     if (upper_rows > INT32_MAX) return fail("add: too many upper rows");
+    lap("level draw");
     if (int rc = h->ensure_capacity(n0 + n, upper_rows)) return rc;
+    lap("ensure_capacity (cudaMalloc)");
 
     // -- storage->add: vectors into HBM; new rows = -1
     BH_CUDA(cudaMemcpyAsync(h->vecs.p + (size_t)n0 * d, x, (size_t)n * d * sizeof(float),
@@ -318,7 +334,11 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
                                 (size_t)(upper_rows - h->n_upper_rows) * M * sizeof(int32_t), h->stream));
     BH_CUDA(cudaMemcpyAsync(h->upper_base_d.p + n0, new_ub.data(), (size_t)n * sizeof(int32_t),
                             cudaMemcpyHostToDevice, h->stream));
+    BH_CUDA(cudaMemsetAsync(h->nver0.p + n0, 0, (size_t)n, h->stream));
+    if (upper_rows > h->n_upper_rows)
+        BH_CUDA(cudaMemsetAsync(h->nverU.p + h->n_upper_rows, 0, (size_t)(upper_rows - h->n_upper_rows), h->stream));
     BH_CUDA(cudaStreamSynchronize(h->stream));  // new_ub / x may go out of scope
+    lap("H2D vectors + row init");
     h->levels.insert(h->levels.end(), new_levels.begin(), new_levels.end());
     h->upper_base.insert(h->upper_base.end(), new_ub.begin(), new_ub.end());
     h->n_upper_rows = upper_rows;
@@ -386,6 +406,7 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
         }
     }
     if (items.empty()) return 0;
+    lap("order + round schedule");
     size_t max_items = 0;
     for (const Round& r : rounds) max_items = std::max(max_items, (size_t)(r.item_end - r.item_begin));
 
@@ -410,6 +431,7 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     BH_CUDA(h->e_next.reserve(max_edges, h->stream));
     BH_CUDA(h->e_dist.reserve(max_edges, h->stream));
 
+    lap("scratch alloc + items H2D");
     BH_CUDA(cudaEventRecord(h->ev0, h->stream));
     for (const Round& r : rounds) {
         const int n_items = (int)(r.item_end - r.item_begin);
@@ -442,6 +464,9 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
             b.edge_next = h->e_next.p;
             b.slot_head = h->slot_head.p;
             b.n_level0 = h->slot_level0;
+            b.nver0 = h->nver0.p;
+            b.nverU = h->nverU.p;
+            b.max_special = std::min(8, std::max(2, (16 * 1024) / (4 * d)));
             BH_CUDA(bh::launch_select_and_link(g, b, h->num_sms, h->stream));
             BH_CUDA(bh::launch_backlinks(g, b, h->num_sms, h->stream));
             bh::count_launch(3);
@@ -452,7 +477,9 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
         }
     }
     BH_CUDA(cudaEventRecord(h->ev1, h->stream));
+    lap("enqueue rounds (host)");
     BH_CUDA(cudaStreamSynchronize(h->stream));
+    lap("wait for device");
     BH_CUDA(cudaEventElapsedTime(&h->last_build_ms, h->ev0, h->ev1));
     return 0;
 }
@@ -568,6 +595,32 @@ int bh_index_search(const bh_index* h, int64_t n, const float* x, int64_t k, flo
         return 0;
     }
     BH_CUDA(cudaSetDevice(h->device));
+    // Zero-copy path: when the caller's buffers are page-locked (cudaHostAlloc / cudaHostRegister,
+    // e.g. torch pinned tensors) they are device-addressable under UVA, so the kernel reads each
+    // query straight from host memory with its TMA bulk copy and writes the k results back over
+    // PCIe — the transfers overlap the traversal instead of bracketing it.
+    if (n <= INT32_MAX && !(params && params->stats)) {
+        auto dev_ptr = [](const void* p) -> void* {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+        };
+        void* xd = dev_ptr(x);
+        void* dd = dev_ptr(distances);
+        void* ld = dev_ptr(labels);
+        if (xd && dd && ld) {
+            BH_CUDA(cudaEventRecord(h->ev0, h->stream));
+            if (int rc = search_device_impl(h, n, (const float*)xd, k, (float*)dd, (int64_t*)ld, nullptr, params))
+                return rc;
+            BH_CUDA(cudaEventRecord(h->ev1, h->stream));
+            BH_CUDA(cudaStreamSynchronize(h->stream));
+            BH_CUDA(cudaEventElapsedTime(&h->last_search_ms, h->ev0, h->ev1));
+            return 0;
+        }
+    }
     const int64_t chunk = 1 << 18;
     const int64_t nb = std::min(n, chunk);
     BH_CUDA(h->q_d.reserve((size_t)nb * h->d, h->stream));
@@ -713,6 +766,8 @@ int bh_index_import_graph(bh_index* h, int64_t n, const float* x, const int32_t*
     if (!up.empty())
         BH_CUDA(cudaMemcpyAsync(h->upper_nbr.p, up.data(), up.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     BH_CUDA(cudaMemcpyAsync(h->upper_base_d.p, ub.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    BH_CUDA(cudaMemsetAsync(h->nver0.p, 0, (size_t)n, h->stream));  // imported rows: nothing verified yet
+    if (upper_rows) BH_CUDA(cudaMemsetAsync(h->nverU.p, 0, (size_t)upper_rows, h->stream));
     BH_CUDA(cudaStreamSynchronize(h->stream));
     h->levels.assign(levels, levels + n);
     h->upper_base = ub;

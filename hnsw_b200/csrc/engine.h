@@ -50,6 +50,11 @@ struct BuildBatch {
     int32_t* edge_next;       // [..] intrusive list link
     int32_t* slot_head;       // [n_slots] head of the per-row pending list, -1 = empty (persistent)
     int64_t n_level0;         // number of level-0 rows (= ntotal capacity used for slot numbering)
+    // verified prefix per row: members at positions [0, nver) are known to be mutually consistent
+    // under the selection heuristic w.r.t. the row owner (see backlink_kernel)
+    uint8_t* nver0;           // [ntotal] level-0 rows
+    uint8_t* nverU;           // [n_upper_rows]
+    int max_special;          // cap on "unverified" candidates handled by the incremental shrink
 };
 
 cudaError_t launch_select_and_link(const GraphView& g, const BuildBatch& b, int num_sms, cudaStream_t stream);

@@ -189,3 +189,18 @@ def test_sharded_index_single_rank_nccl(small_l2):
         assert sh.ntotal == 4000
     finally:
         dist.destroy_process_group()
+
+
+def test_pinned_host_buffers_zero_copy_path(small_l2):
+    """Page-locked caller buffers take the zero-copy path (kernel reads/writes host memory);
+    results must equal the staged path."""
+    import torch
+    idx = _gpu_from_oracle(small_l2["oracle"], small_l2["xb"], 16)
+    xq = small_l2["xq"]
+    D0, I0 = idx.search(xq, 10, efSearch=48)
+    xp = torch.empty(xq.shape, dtype=torch.float32).pin_memory()
+    xp.copy_(torch.from_numpy(xq))
+    Dp = torch.empty(len(xq), 10, dtype=torch.float32).pin_memory()
+    Ip = torch.empty(len(xq), 10, dtype=torch.int64).pin_memory()
+    D1, I1 = idx.search(xp.numpy(), 10, efSearch=48, out=(Dp.numpy(), Ip.numpy()))
+    assert np.array_equal(I1, I0) and np.array_equal(D1, D0)
