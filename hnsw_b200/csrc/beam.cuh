@@ -29,37 +29,36 @@ struct BeamStats {
 struct GroupSmem {
     uint64_t* mbar;
     float4* qbuf;
-    unsigned long long* list[2];
-    int32_t* cand_id;
-    unsigned long long* cand_key;
-    unsigned long long* acc_key;
-    int32_t* ctrl;  // [0]=n_new / stop, [1]=lsize, [2]=cur, [3]=work index
+    unsigned long long* list;      // [ef] sorted keys, merged in place
+    int32_t* cand_id;              // [deg] ids to score this hop; reused for merge positions
+    unsigned long long* cand_key;  // [deg]
+    unsigned long long* acc_key;   // [deg]
+    int32_t* ctrl;  // [0]=n_new / stop, [1]=lsize, [3]=work index
     uint32_t* hash;
 };
 
 __host__ __device__ inline size_t round16(size_t x) { return (x + 15) & ~size_t(15); }
 
-__host__ __device__ inline size_t group_smem_bytes(int d, int ef, int hash_slots) {
-    return 16 + round16((size_t)d * 4) + 2 * round16((size_t)ef * 8) + round16(kMaxDeg * 4) +
-           2 * round16(kMaxDeg * 8) + 32 + (size_t)hash_slots * 4;
+// deg = longest adjacency row (2M)
+__host__ __device__ inline size_t group_smem_bytes(int d, int ef, int hash_slots, int deg) {
+    return 16 + round16((size_t)d * 4) + round16((size_t)ef * 8) + round16((size_t)deg * 4) +
+           2 * round16((size_t)deg * 8) + 32 + (size_t)hash_slots * 4;
 }
 
-__device__ inline GroupSmem carve_group_smem(unsigned char* p, int d, int ef, int hash_slots) {
+__device__ inline GroupSmem carve_group_smem(unsigned char* p, int d, int ef, int hash_slots, int deg) {
     GroupSmem s;
     s.mbar = reinterpret_cast<uint64_t*>(p);
     p += 16;
     s.qbuf = reinterpret_cast<float4*>(p);
     p += round16((size_t)d * 4);
-    s.list[0] = reinterpret_cast<unsigned long long*>(p);
-    p += round16((size_t)ef * 8);
-    s.list[1] = reinterpret_cast<unsigned long long*>(p);
+    s.list = reinterpret_cast<unsigned long long*>(p);
     p += round16((size_t)ef * 8);
     s.cand_id = reinterpret_cast<int32_t*>(p);
-    p += round16(kMaxDeg * 4);
+    p += round16((size_t)deg * 4);
     s.cand_key = reinterpret_cast<unsigned long long*>(p);
-    p += round16(kMaxDeg * 8);
+    p += round16((size_t)deg * 8);
     s.acc_key = reinterpret_cast<unsigned long long*>(p);
-    p += round16(kMaxDeg * 8);
+    p += round16((size_t)deg * 8);
     s.ctrl = reinterpret_cast<int32_t*>(p);
     p += 32;
     s.hash = reinterpret_cast<uint32_t*>(p);
@@ -277,15 +276,15 @@ struct Beam {
     // ef_stop  stop when the popped entry has >= ef_stop list entries before it
     //          (faiss count_below test; INT_MAX disables)
     // max_steps  faiss `!check_relative_distance && nstep > efSearch` (INT_MAX disables)
-    // On return ctrl[1] = list size, ctrl[2] = index of the live list buffer.
+    // On return ctrl[1] = list size.
     __device__ void run(int level, int ef, int ef_stop, int max_steps, int hash_bits, uint32_t start_id,
                         float start_d, BeamStats& st) const {
-        int lsize = 0, cur = 0, cursor = 0, hcount = 0, nstep = 0;
+        int lsize = 0, cursor = 0, hcount = 0, nstep = 0;
         const int hlimit = (3 << hash_bits) >> 2;  // reset above 75 % load
         if (wig == 0) {
             hash_clear(hash_bits);
             if (lane == 0) {
-                s.list[0][0] = pack_key(start_d, start_id);
+                s.list[0] = pack_key(start_d, start_id);
                 hash_test_and_set(start_id, hash_bits);
             }
             lsize = 1;
@@ -296,7 +295,7 @@ struct Beam {
             if (wig == 0) {
                 // -- pop_min: first unexpanded entry of the sorted list
                 int pos = -1;
-                const unsigned long long* L = s.list[cur];
+                const unsigned long long* L = s.list;
                 for (int b = cursor & ~31; b < lsize; b += 32) {
                     const int i = b + lane;
                     const bool un = i >= cursor && i < lsize && !(L[i] & kExpanded);
@@ -310,7 +309,7 @@ struct Beam {
                 if (pos >= 0 && pos < ef_stop && nstep <= max_steps) {
                     const uint32_t v0 = key_id(L[pos]);
                     __syncwarp();
-                    if (lane == 0) s.list[cur][pos] = L[pos] | kExpanded;
+                    if (lane == 0) s.list[pos] = L[pos] | kExpanded;
                     cursor = pos + 1;
                     int ids[kMaxIdsPerLane];
                     load_row((int)v0, level, ids);
@@ -341,23 +340,23 @@ struct Beam {
             if (n_new < 0) break;
             compute_dists(n_new);
             group_sync();
-            if (wig == 0 && n_new > 0) merge(n_new, ef, lsize, cur, cursor);
+            if (wig == 0 && n_new > 0) merge(n_new, ef, lsize, cursor);
         }
         if (wig == 0) {
-            if (lane == 0) {
-                s.ctrl[1] = lsize;
-                s.ctrl[2] = cur;
-            }
+            if (lane == 0) s.ctrl[1] = lsize;
             __syncwarp();
         }
     }
 
-    // Merge the hop's scored candidates into the sorted list (leader warp).
+    // Merge the hop's scored candidates into the sorted list, in place (leader warp).
     // Equivalent to pushing them one by one into faiss's bounded MinimaxHeap: the list ends up
     // holding the ef smallest keys of (list ∪ candidates); on exact distance ties the id breaks it.
-    __device__ __forceinline__ void merge(int n_new, int ef, int& lsize, int& cur, int& cursor) const {
-        const unsigned long long* L = s.list[cur];
-        unsigned long long* O = s.list[cur ^ 1];
+    // Every old entry moves right by the number of accepted keys below it, so the list is walked
+    // from its tail in 32-entry chunks (read chunk, sync, write chunk: a chunk's writes land at or
+    // above its own base, i.e. only on slots already vacated); entries below the smallest
+    // insertion point are not touched at all; accepted keys drop into the holes at the end.
+    __device__ __forceinline__ void merge(int n_new, int ef, int& lsize, int& cursor) const {
+        unsigned long long* L = s.list;
         const bool full = lsize == ef;
         const unsigned long long thr = full ? key_clean(L[ef - 1]) : ~0ull;
         int n_acc = 0;
@@ -375,6 +374,7 @@ struct Beam {
         }
         if (n_acc == 0) return;
         __syncwarp();
+        int* acc_pos = s.cand_id;  // free again: the hop's ids have been scored
         int minpos = ef;
         unsigned long long minacc = ~0ull;
         for (int a = lane; a < n_acc; a += 32) {
@@ -387,7 +387,7 @@ struct Beam {
                 if (key_clean(L[mid]) < ka) lo = mid + 1; else hi = mid;
             }
             const int pos = ra + lo;
-            if (pos < ef) O[pos] = ka;
+            acc_pos[a] = pos;
             minpos = pos < minpos ? pos : minpos;
             minacc = ka < minacc ? ka : minacc;
         }
@@ -398,18 +398,31 @@ struct Beam {
             const unsigned long long oa = __shfl_xor_sync(0xffffffffu, minacc, off);
             minacc = oa < minacc ? oa : minacc;
         }
-        for (int i = lane; i < lsize; i += 32) {
-            const unsigned long long e = L[i];
-            const unsigned long long ec = key_clean(e);
-            int cnt = 0;
-            if (ec > minacc)
-                for (int b2 = 0; b2 < n_acc; b2++) cnt += s.acc_key[b2] < ec;
-            const int np = i + cnt;
-            if (np < ef) O[np] = e;
+        __syncwarp();
+        if (lsize > 0) {
+            for (int b = (lsize - 1) & ~31; b >= (minpos & ~31); b -= 32) {
+                const int i = b + lane;
+                unsigned long long e = 0;
+                int np = ef;
+                if (i < lsize) {
+                    e = L[i];
+                    const unsigned long long ec = key_clean(e);
+                    int cnt = 0;
+                    if (ec > minacc)
+                        for (int b2 = 0; b2 < n_acc; b2++) cnt += s.acc_key[b2] < ec;
+                    np = i + cnt;
+                }
+                __syncwarp();
+                if (np < ef) L[np] = e;
+                __syncwarp();
+            }
+        }
+        for (int a = lane; a < n_acc; a += 32) {
+            const int pos = acc_pos[a];
+            if (pos < ef) L[pos] = s.acc_key[a];
         }
         lsize = lsize + n_acc < ef ? lsize + n_acc : ef;
         cursor = minpos < cursor ? minpos : cursor;
-        cur ^= 1;
         __syncwarp();
     }
 };

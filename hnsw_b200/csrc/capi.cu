@@ -162,7 +162,7 @@ struct bh_index {
         const int lo = min_hash_bits(ef);
         if (req > 0) return std::min(std::max(req, lo), 16);
         // measured on 1M x 128 (profiles/README.md): ~4 slots per list entry is the sweet spot
-        int b = ceil_log2((long long)ef * 4);
+        int b = std::min(ceil_log2((long long)ef * 4), 10);
         b = std::max(b, 9);
         return std::min(std::max(b, lo), 15);
     }
@@ -170,7 +170,7 @@ struct bh_index {
         if (req == 1 || req == 2 || req == 4 || req == 8) return req;
         // one warp per query keeps the most queries in flight; go wider only when a single
         // query's state no longer fits beside three others in one SM's shared memory
-        const size_t s = bh::beam_group_smem(d, ef, hash_bits);
+        const size_t s = bh::beam_group_smem(d, ef, hash_bits, deg0());
         if (4 * s <= smem_optin) return 1;
         if (2 * s <= smem_optin) return 2;
         return 4;
@@ -180,7 +180,7 @@ struct bh_index {
     int beam_variant(int ef, int hash_bits) const {
         const char* e = getenv("BH_BEAM_VARIANT");
         if (e) return atoi(e);
-        return 24 * bh::beam_group_smem(d, ef, hash_bits) <= smem_optin - 6 * 1024 ? 1 : 0;
+        return 24 * bh::beam_group_smem(d, ef, hash_bits, deg0()) <= smem_optin - 6 * 1024 ? 1 : 0;
     }
 
     int ensure_capacity(int64_t n_new_total, int64_t upper_rows_total) {
@@ -230,7 +230,7 @@ int search_device_impl(const bh_index* h, int64_t n, const float* xq_d, int64_t 
     const int hb = h->auto_hash_bits(ef, params ? params->hash_bits : 0);
     const int W = h->auto_warps(ef, hb, params ? params->warps_per_query : 0);
     const int G = W >= 4 ? 1 : 4 / W;
-    if (G * bh::beam_group_smem(h->d, ef, hb) > h->smem_optin)
+    if (G * bh::beam_group_smem(h->d, ef, hb, h->deg0()) > h->smem_optin)
         return fail("efSearch/hash_bits need more shared memory than one SM has");
     bh::BeamTask t{};
     t.queries = xq_d;
@@ -415,7 +415,7 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     const int hb = h->auto_hash_bits(efc, h->bp.hash_bits);
     const int W = h->auto_warps(efc, hb, h->bp.warps_per_query);
     const int G = W >= 4 ? 1 : 4 / W;
-    if (G * bh::beam_group_smem(d, efc, hb) > h->smem_optin)
+    if (G * bh::beam_group_smem(d, efc, hb, deg0) > h->smem_optin)
         return fail("efConstruction/hash_bits need more shared memory than one SM has");
 
     BH_CUDA(h->items_d.reserve(items.size(), h->stream));

@@ -30,7 +30,7 @@ struct BeamTask {
 };
 
 int team_for_dim(int d);
-size_t beam_group_smem(int d, int ef, int hash_bits);
+size_t beam_group_smem(int d, int ef, int hash_bits, int deg);
 cudaError_t launch_beam(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
                         cudaStream_t stream, int* grid_out);
 
