@@ -247,8 +247,9 @@ def run_b200(a):
     # ---- data: every rank indexes the SAME database (replicas) and answers its own query set
     xb, xq = make_data(a, rank)
     xb_t, xq_t = torch.from_numpy(xb).to(dev), torch.from_numpy(xq).to(dev)
-    _, gt_t = exact_knn_torch(xb_t, xq_t, a.k)
+    _, gt_t = exact_knn_torch(xb_t, xq_t, a.k, chunk=1 << 16)
     gt = gt_t.cpu().numpy()
+    torch.cuda.empty_cache()  # give the brute-force scratch back before the index allocates
 
     # ---- build (add): vectors/sec, wall clock around the public call (H2D included)
     idx = hnsw_b200.IndexHNSWFlat(a.d, a.M, hnsw_b200.METRIC_L2, device=local)

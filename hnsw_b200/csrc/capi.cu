@@ -419,10 +419,13 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
         return fail("efConstruction/hash_bits need more shared memory than one SM has");
 
     BH_CUDA(h->items_d.reserve(items.size(), h->stream));
+    lap("  items alloc");
     BH_CUDA(cudaMemcpyAsync(h->items_d.p, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice,
                             h->stream));
+    lap("  items H2D");
     BH_CUDA(h->cand_lists.reserve(max_items * efc, h->stream));
     BH_CUDA(h->cand_counts.reserve(max_items, h->stream));
+    lap("  cand alloc");
     const size_t max_edges = max_items * deg0;
     BH_CUDA(h->e_slot.reserve(max_edges, h->stream));
     BH_CUDA(h->e_src.reserve(max_edges, h->stream));
