@@ -35,6 +35,12 @@ EF_GRID = [16, 24, 32, 48, 64, 96, 128, 192, 256, 384, 512]
 METRIC_NAME = "QPS at recall@10>=0.95 (1M x128 L2)"
 
 
+def workload_name(a):
+    shape = "SIFT1M-shape" if (a.n, a.d, a.ip) == (1_000_000, 128, False) else "custom-shape"
+    return (f"{shape} {a.n}x{a.d} fp32 {'IP' if a.ip else 'L2'}, M={a.M} efC={a.efc}, "
+            f"{a.nq}-query batch, k={a.k}")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -51,6 +57,7 @@ def parse():
     ap.add_argument("--target-recall", type=float, default=0.95)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sharded", action="store_true")
+    ap.add_argument("--ip", action="store_true", help="inner-product metric on L2-normalised rows (other BASELINE shapes)")
     return ap.parse_args()
 
 
@@ -132,7 +139,7 @@ def make_data(a, rank=0):
     """Database + this rank's query set. The pool of QUERY_POOL x nq queries and the database come
     from ONE seeded draw, so xb is bit-identical for every N and every rank; rank r takes slice r."""
     from hnsw_b200.datasets import synthetic_dataset
-    xb, xq_all = synthetic_dataset(a.d, a.n, QUERY_POOL * a.nq, d1=a.d1, seed=1338)
+    xb, xq_all = synthetic_dataset(a.d, a.n, QUERY_POOL * a.nq, d1=a.d1, seed=1338, normalize=a.ip)
     r = rank % QUERY_POOL
     return xb, np.ascontiguousarray(xq_all[r * a.nq:(r + 1) * a.nq])
 
@@ -157,7 +164,7 @@ def run_reference(a):
     threads = os.cpu_count() or 1
     xb, xq = make_data(a, 0)
     # bounded build: calibrate on 50k vectors, keep the whole build under ~120 s
-    o = om.OracleHNSWFlat(a.d, a.M, om.METRIC_L2, lib_path=path)
+    o = om.OracleHNSWFlat(a.d, a.M, om.METRIC_INNER_PRODUCT if a.ip else om.METRIC_L2, lib_path=path)
     o.efConstruction = a.efc
     o.threads = threads
     n_cal = min(a.n, 50_000)
@@ -175,7 +182,7 @@ def run_reference(a):
     xb = xb[:n_ref]
     import torch  # CPU tensors only: exact ground truth by chunked GEMM
     from hnsw_b200.datasets import exact_knn_torch
-    _, gt = exact_knn_torch(torch.from_numpy(xb), torch.from_numpy(xq), a.k, chunk=1 << 15)
+    _, gt = exact_knn_torch(torch.from_numpy(xb), torch.from_numpy(xq), a.k, inner_product=a.ip, chunk=1 << 15)
     gt = gt.numpy()
     ef_sel, rec_sel, sweep = None, None, []
     for ef in EF_GRID:
@@ -202,7 +209,7 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC_NAME, "value": round(qps, 1), "unit": "queries/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(dt / a.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"SIFT1M-shape {a.n}x{a.d} fp32 L2, M={a.M} efC={a.efc}, {a.nq}-query batch, k={a.k}",
+        "config": {"workload": workload_name(a),
                    "efSearch": ef_sel, "recall_at_10": round(rec_sel, 4), "d1": a.d1, "seed": 1338,
                    "n_indexed": n_ref},
         "build_vectors_per_s": round(n_ref / t_build, 1), "ef_sweep": sweep,
@@ -247,12 +254,12 @@ def run_b200(a):
     # ---- data: every rank indexes the SAME database (replicas) and answers its own query set
     xb, xq = make_data(a, rank)
     xb_t, xq_t = torch.from_numpy(xb).to(dev), torch.from_numpy(xq).to(dev)
-    _, gt_t = exact_knn_torch(xb_t, xq_t, a.k, chunk=1 << 16)
+    _, gt_t = exact_knn_torch(xb_t, xq_t, a.k, inner_product=a.ip, chunk=1 << 16)
     gt = gt_t.cpu().numpy()
     torch.cuda.empty_cache()  # give the brute-force scratch back before the index allocates
 
     # ---- build (add): vectors/sec, wall clock around the public call (H2D included)
-    idx = hnsw_b200.IndexHNSWFlat(a.d, a.M, hnsw_b200.METRIC_L2, device=local)
+    idx = hnsw_b200.IndexHNSWFlat(a.d, a.M, hnsw_b200.METRIC_INNER_PRODUCT if a.ip else hnsw_b200.METRIC_L2, device=local)
     idx.hnsw.efConstruction = a.efc
     barrier()
     l0 = hnsw_b200.launch_count()
@@ -340,7 +347,7 @@ def run_b200(a):
     if world > 1 and not a.no_sharded:
         n_sh = a.n // world
         lo = rank * n_sh
-        shard = hnsw_b200.IndexHNSWFlat(a.d, a.M, hnsw_b200.METRIC_L2, device=local)
+        shard = hnsw_b200.IndexHNSWFlat(a.d, a.M, hnsw_b200.METRIC_INNER_PRODUCT if a.ip else hnsw_b200.METRIC_L2, device=local)
         shard.hnsw.efConstruction = a.efc
         shard.add(xb[lo:lo + n_sh])
         sstream = torch.cuda.ExternalStream(shard.stream_ptr, device=dev)
@@ -363,7 +370,7 @@ def run_b200(a):
             cur.wait_stream(sstream)
             dist.all_gather_into_tensor(Dg, Dl)
             dist.all_gather_into_tensor(Ig, Il)
-            hnsw_b200.merge_topk_device(Dg.data_ptr(), Ig.data_ptr(), world, a.nq, a.k, hnsw_b200.METRIC_L2,
+            hnsw_b200.merge_topk_device(Dg.data_ptr(), Ig.data_ptr(), world, a.nq, a.k, hnsw_b200.METRIC_INNER_PRODUCT if a.ip else hnsw_b200.METRIC_L2,
                                         offs, Dm.data_ptr(), Im.data_ptr(), cur.cuda_stream)
 
         for _ in range(3):
@@ -390,7 +397,7 @@ def run_b200(a):
         try:
             om, path = native_oracle()
             g = idx.export_graph()
-            o = om.OracleHNSWFlat(a.d, a.M, om.METRIC_L2, lib_path=path)
+            o = om.OracleHNSWFlat(a.d, a.M, om.METRIC_INNER_PRODUCT if a.ip else om.METRIC_L2, lib_path=path)
             o.import_graph(xb, g["levels"], g["neighbors"], g["entry_point"], g["max_level"])
             o.threads = os.cpu_count() or 1
             o.search(xq[:2000], a.k, ef_sel)
@@ -401,7 +408,7 @@ def run_b200(a):
                 best = max(best, a.nq / (time.time() - t0))
                 reps += 1
             # CPU build rate on a bounded sample (first 50k vectors of the same data)
-            ob = om.OracleHNSWFlat(a.d, a.M, om.METRIC_L2, lib_path=path)
+            ob = om.OracleHNSWFlat(a.d, a.M, om.METRIC_INNER_PRODUCT if a.ip else om.METRIC_L2, lib_path=path)
             ob.efConstruction = a.efc
             ob.threads = o.threads
             nb_s = min(a.n, 50_000)
@@ -430,8 +437,7 @@ def run_b200(a):
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": round(ms_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"SIFT1M-shape {a.n}x{a.d} fp32 L2, M={a.M} efC={a.efc}, {a.nq}-query batch, "
-                                   f"k={a.k}" + ("" if world == 1 else f"; {world} replicas, each GPU its own "
+            "config": {"workload": workload_name(a) + ("" if world == 1 else f"; {world} replicas, each GPU its own "
                                                                         f"{a.n}-vector index and {a.nq} queries"),
                        "efSearch": ef_sel, "recall_at_10": round(rec_timed, 4),
                        "recall_at_10_min_over_ranks": round(rec_min, 4), "d1": a.d1, "seed": 1338,

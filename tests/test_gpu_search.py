@@ -204,3 +204,31 @@ def test_pinned_host_buffers_zero_copy_path(small_l2):
     Ip = torch.empty(len(xq), 10, dtype=torch.int64).pin_memory()
     D1, I1 = idx.search(xp.numpy(), 10, efSearch=48, out=(Dp.numpy(), Ip.numpy()))
     assert np.array_equal(I1, I0) and np.array_equal(D1, D0)
+
+
+def test_baseline_config0_plumbing(oracle_mod):
+    """BASELINE.json configs[0]: IndexHNSWFlat M=16 efC=40 on 100k x 128 synthetic fp32 L2, 1k queries,
+    k=10, efSearch=64 — the reference's own CPU-runnable case. CPU-built graph searched on the GPU:
+    identical ids / distances; GPU-built graph: recall within 0.5 pt of the CPU build."""
+    import hnsw_b200
+    d, M, n, nq, k, ef = 128, 16, 100_000, 1000, 10, 64
+    xb, xq = synthetic_dataset(d, n, nq)                 # upstream recipe: d1=10, seed=1338
+    o = oracle_mod.OracleHNSWFlat(d, M)
+    o.efConstruction = 40
+    o.threads = 8
+    o.add(xb)
+    o.set_team(8)                                         # search with the CUDA summation order
+    Do, Io, So = o.search(xq, k, ef, stats=True)
+    idx = _gpu_from_oracle(o, xb, M)
+    D, I, S = idx.search(xq, k, efSearch=ef, stats=True, hash_bits=13)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do) and np.array_equal(S, So)
+    import torch
+    from hnsw_b200.datasets import exact_knn_torch
+    _, gt = exact_knn_torch(torch.from_numpy(xb).cuda(), torch.from_numpy(xq).cuda(), k)
+    gt = gt.cpu().numpy()
+    g = hnsw_b200.IndexHNSWFlat(d, M)
+    g.hnsw.efConstruction = 40
+    g.add(xb)
+    r_cpu = oracle_mod.recall_at_k(Io, gt)
+    r_gpu = oracle_mod.recall_at_k(g.search(xq, k, efSearch=ef)[1], gt)
+    assert r_cpu > 0.9 and r_gpu >= r_cpu - 0.005, (r_cpu, r_gpu)
