@@ -51,6 +51,7 @@ _SIGS = {
     "bh_index_search": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, _P, C.POINTER(SearchParams)]),
     "bh_index_search_device": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, _P, C.POINTER(SearchParams)]),
     "bh_index_reconstruct": (C.c_int, [_P, C.c_int64, _P]),
+    "bh_index_reconstruct_n": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
     "bh_index_ntotal": (C.c_int64, [_P]),
     "bh_index_d": (C.c_int, [_P]),
     "bh_index_M": (C.c_int, [_P]),

@@ -667,6 +667,17 @@ int bh_index_reconstruct(const bh_index* h, int64_t key, float* out) {
     return 0;
 }
 
+int bh_index_reconstruct_n(const bh_index* h, int64_t i0, int64_t ni, float* out) {
+    if (!h) return fail("null index");
+    if (i0 < 0 || ni < 0 || i0 + ni > h->ntotal) return fail("reconstruct_n: range out of bounds");
+    if (ni == 0) return 0;
+    BH_CUDA(cudaSetDevice(h->device));
+    BH_CUDA(cudaMemcpyAsync(out, h->vecs.p + (size_t)i0 * h->d, (size_t)ni * h->d * sizeof(float),
+                            cudaMemcpyDeviceToHost, h->stream));
+    BH_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 int64_t bh_index_ntotal(const bh_index* h) { return h ? h->ntotal : -1; }
 int bh_index_d(const bh_index* h) { return h ? h->d : -1; }
 int bh_index_M(const bh_index* h) { return h ? h->M : -1; }

@@ -145,6 +145,13 @@ class IndexHNSWFlat:
         _lib.check(_lib.lib().bh_index_reconstruct(self._h, int(key), out.ctypes.data))
         return out
 
+    def reconstruct_n(self, i0: int = 0, ni: int | None = None):
+        """faiss Index.reconstruct_n: rows [i0, i0+ni) of the stored vectors."""
+        ni = self.ntotal - i0 if ni is None else ni
+        out = np.empty((ni, self.d), np.float32)
+        _lib.check(_lib.lib().bh_index_reconstruct_n(self._h, int(i0), int(ni), out.ctypes.data))
+        return out
+
     # ---- engine extras
     def set_build_params(self, max_batch=0, batch_divisor=0, warps_per_query=0, hash_bits=0):
         p = BuildParams(int(max_batch), int(batch_divisor), int(warps_per_query), int(hash_bits))

@@ -74,6 +74,8 @@ int bh_index_search_device(const bh_index* h, int64_t n, const float* x, int64_t
                            float* distances, int64_t* labels, const bh_search_params* params);
 /* replaces faiss::IndexHNSW::reconstruct */
 int bh_index_reconstruct(const bh_index* h, int64_t key, float* out);
+/* replaces faiss::Index::reconstruct_n(i0, ni, recons) */
+int bh_index_reconstruct_n(const bh_index* h, int64_t i0, int64_t ni, float* out);
 
 /* -- fields (faiss: index.d, index.ntotal, index.hnsw.efSearch, …) ---------------- */
 int64_t bh_index_ntotal(const bh_index* h);
