@@ -166,14 +166,22 @@ struct bh_index {
         b = std::max(b, 9);
         return std::min(std::max(b, lo), 15);
     }
-    int auto_warps(int ef, int hash_bits, int req) const {
+    // Warps cooperating on one query. With enough work items to fill the GPU, one warp per query
+    // keeps the most queries in flight (throughput regime). With few items (small query batches,
+    // the early construction rounds) the machine is idle and a hop's latency is what matters:
+    // W warps score a hop's ~50 vectors in one gather round instead of 3-6 serial ones.
+    int auto_warps(int ef, int hash_bits, int req, long long n_items) const {
         if (req == 1 || req == 2 || req == 4 || req == 8) return req;
-        // one warp per query keeps the most queries in flight; go wider only when a single
-        // query's state no longer fits beside three others in one SM's shared memory
         const size_t s = bh::beam_group_smem(d, ef, hash_bits, deg0());
-        if (4 * s <= smem_optin) return 1;
-        if (2 * s <= smem_optin) return 2;
-        return 4;
+        // measured on an idle B200 (scripts/small_batch.py): 11 us/hop at W=1, 6.5-7 us at W=4;
+        // W=8 never wins, and beyond ~1k items W=1's higher residency wins.
+        int w = 1;
+        if (n_items <= 3LL * num_sms) w = 4;
+        else if (n_items <= 5LL * num_sms) w = 2;
+        // one warp per query needs four queries' state per CTA
+        if (w == 1 && 4 * s > smem_optin) w = 2;
+        if (w == 2 && 2 * s > smem_optin) w = 4;
+        return w;
     }
     // Register/occupancy variant of the one-warp-per-query kernel (beam_kernel.cu): 1 = 80 regs,
     // 6 CTAs/SM, used while 24 queries' state fits in one SM's shared memory; else 0 = 128 regs, 4 CTAs.
@@ -228,7 +236,7 @@ int search_device_impl(const bh_index* h, int64_t n, const float* xq_d, int64_t 
     const int ef = (int)std::max<int64_t>(efS, k);
     if (ef > 4096) return fail("max(efSearch, k) > 4096 is not supported");
     const int hb = h->auto_hash_bits(ef, params ? params->hash_bits : 0);
-    const int W = h->auto_warps(ef, hb, params ? params->warps_per_query : 0);
+    const int W = h->auto_warps(ef, hb, params ? params->warps_per_query : 0, n);
     const int G = W >= 4 ? 1 : 4 / W;
     if (G * bh::beam_group_smem(h->d, ef, hb, h->deg0()) > h->smem_optin)
         return fail("efSearch/hash_bits need more shared memory than one SM has");
@@ -413,9 +421,7 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     const int efc = h->efConstruction;
     if (efc < 1 || efc > 4096) return fail("efConstruction must be in [1, 4096]");
     const int hb = h->auto_hash_bits(efc, h->bp.hash_bits);
-    const int W = h->auto_warps(efc, hb, h->bp.warps_per_query);
-    const int G = W >= 4 ? 1 : 4 / W;
-    if (G * bh::beam_group_smem(d, efc, hb, deg0) > h->smem_optin)
+    if (bh::beam_group_smem(d, efc, hb, deg0) > h->smem_optin)
         return fail("efConstruction/hash_bits need more shared memory than one SM has");
 
     BH_CUDA(h->items_d.reserve(items.size(), h->stream));
@@ -452,6 +458,7 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
             t.stats = nullptr;
             t.counter = h->counter.p;
             BH_CUDA(cudaMemsetAsync(h->counter.p, 0, sizeof(int), h->stream));
+            const int W = h->auto_warps(efc, hb, h->bp.warps_per_query, n_items);
             BH_CUDA(bh::launch_beam(g, t, W, h->beam_variant(efc, hb), h->num_sms, h->stream, nullptr));
             bh::BuildBatch b{};
             b.items = t.items;
