@@ -100,9 +100,34 @@ struct Beam {
     // Team t scores rows t, t+NT, …; R rows' worth of 128-bit gathers are issued before
     // the first is consumed.
     __device__ __forceinline__ void compute_dists(int n) const {
+        if (g.nchunk == TEAM * CPL)
+            compute_dists_impl<true>(n);   // every lane owns exactly CPL chunks: no per-chunk predicate
+        else
+            compute_dists_impl<false>(n);
+    }
+
+    template <int C>
+    __device__ __forceinline__ void load_chunks(float4 (&x)[CPL], const float4* rowp, bool ok, int lit) const {
+        if constexpr (C < CPL) {
+            x[C] = (ok && (C * TEAM + lit) < g.nchunk) ? ldg_stream_off<C * TEAM * 16>(rowp)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            load_chunks<C + 1>(x, rowp, ok, lit);
+        }
+    }
+    template <int C>
+    __device__ __forceinline__ void load_chunks_full(float4 (&x)[CPL], const float4* rowp) const {
+        if constexpr (C < CPL) {
+            x[C] = ldg_stream_off<C * TEAM * 16>(rowp);
+            load_chunks_full<C + 1>(x, rowp);
+        }
+    }
+
+    template <bool FULL>
+    __device__ __forceinline__ void compute_dists_impl(int n) const {
         const int lit = lane % TEAM;
         const int team = wig * TPW + lane / TEAM;
-        const float4* __restrict__ base = reinterpret_cast<const float4*>(g.vecs);
+        const float4* __restrict__ base = reinterpret_cast<const float4*>(g.vecs) + lit;
+        const bool l2 = g.is_l2 != 0;
         for (int r0 = 0; r0 < n; r0 += NT * R) {
             float4 x[R][CPL];
             int id[R];
@@ -113,20 +138,17 @@ struct Beam {
             }
 #pragma unroll
             for (int k = 0; k < R; k++) {
-                const float4* row = base + (size_t)(id[k] < 0 ? 0 : id[k]) * g.nchunk;
-#pragma unroll
-                for (int c = 0; c < CPL; c++) {
-                    const int chunk = c * TEAM + lit;
-                    if (id[k] >= 0 && chunk < g.nchunk)
-                        x[k][c] = ldg_stream(row + chunk);
-                    else
-                        x[k][c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                // rows past the end re-read row 0 (always valid) instead of branching around the loads
+                const float4* rowp = base + (size_t)(id[k] < 0 ? 0 : id[k]) * g.nchunk;
+                if (FULL)
+                    load_chunks_full<0>(x[k], rowp);
+                else
+                    load_chunks<0>(x[k], rowp, true, lit);
             }
 #pragma unroll
             for (int k = 0; k < R; k++) {
                 float acc = 0.f;
-                if (g.is_l2) {
+                if (l2) {
 #pragma unroll
                     for (int c = 0; c < CPL; c++) {
                         float t;
@@ -147,7 +169,7 @@ struct Beam {
 #pragma unroll
                 for (int off = TEAM / 2; off >= 1; off >>= 1)
                     acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
-                if (!g.is_l2) acc = -acc;
+                if (!l2) acc = -acc;
                 if (lit == 0 && id[k] >= 0) s.cand_key[r0 + k * NT + team] = pack_key(acc, (uint32_t)id[k]);
             }
         }
