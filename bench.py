@@ -234,6 +234,7 @@ def run_reference(a):
     t_build = t_cal + (time.time() - t0)
     xb = xb[:n_ref]
     import torch  # CPU tensors only: exact ground truth by chunked GEMM
+    torch.set_num_threads(threads)  # torchrun exports OMP_NUM_THREADS=1; the GEMM should use the box
     from hnsw_b200.datasets import exact_knn_torch
     _, gt = exact_knn_torch(torch.from_numpy(xb), torch.from_numpy(xq), a.k, inner_product=a.ip, chunk=1 << 15)
     gt = gt.numpy()

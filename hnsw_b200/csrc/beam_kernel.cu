@@ -119,7 +119,8 @@ cudaError_t launch_one(const GraphView& g, const BeamTask& t, int num_sms, cudaS
 }
 
 // variant (W == 1 only): 0 = R rows in flight per team, 4 blocks/SM (<=128 regs);
-// 1 = R/2 rows, 6 blocks/SM (<=80 regs); 2 = R/2 rows, 8 blocks/SM (<=64 regs).
+// 1 = R/2 rows, 6 blocks/SM (<=80 regs); 2 = R/2 rows, 8 blocks/SM (<=64 regs);
+// 3 = R/2 rows, 5 blocks/SM (<=96 regs).
 template <int TEAM, int CPL, int R>
 cudaError_t launch_w(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
                      cudaStream_t stream, int* grid_out) {
@@ -128,6 +129,7 @@ cudaError_t launch_w(const GraphView& g, const BeamTask& t, int W, int variant, 
         case 1:
             if (variant == 1) return launch_one<TEAM, CPL, 1, RH, 4, 6>(g, t, num_sms, stream, grid_out);
             if (variant == 2) return launch_one<TEAM, CPL, 1, RH, 4, 8>(g, t, num_sms, stream, grid_out);
+            if (variant == 3) return launch_one<TEAM, CPL, 1, RH, 4, 5>(g, t, num_sms, stream, grid_out);
             return launch_one<TEAM, CPL, 1, R, 4, 4>(g, t, num_sms, stream, grid_out);
         case 2: return launch_one<TEAM, CPL, 2, R, 2, 1>(g, t, num_sms, stream, grid_out);
         case 4: return launch_one<TEAM, CPL, 4, R, 1, 1>(g, t, num_sms, stream, grid_out);

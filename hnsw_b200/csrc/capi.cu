@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <random>
 #include <string>
 #include <vector>
@@ -81,6 +82,7 @@ struct bh_index {
     int efSearch = 16, efConstruction = 40;  // faiss HNSW defaults (App. A.1)
     bool check_relative_distance = true;
     bh_build_params bp{0, 0, 0, 0};
+    mutable std::mutex mu;  // one operation at a time per handle (stream, counter and staging are shared)
     std::vector<double> assign_probas;
     std::vector<int> cum_nn;
     std::mt19937 rng{12345};
@@ -184,11 +186,15 @@ struct bh_index {
         return w;
     }
     // Register/occupancy variant of the one-warp-per-query kernel (beam_kernel.cu): 1 = 80 regs,
-    // 6 CTAs/SM, used while 24 queries' state fits in one SM's shared memory; else 0 = 128 regs, 4 CTAs.
+    // 6 CTAs/SM, used while 24 queries' state fits in one SM's shared memory; then 3 = 96 regs, 5 CTAs;
+    // else 0 = 128 regs, 4 CTAs.
     int beam_variant(int ef, int hash_bits) const {
         const char* e = getenv("BH_BEAM_VARIANT");
         if (e) return atoi(e);
-        return 24 * bh::beam_group_smem(d, ef, hash_bits, deg0()) <= smem_optin - 6 * 1024 ? 1 : 0;
+        const size_t gs = bh::beam_group_smem(d, ef, hash_bits, deg0());
+        if (24 * gs <= smem_optin - 6 * 1024) return 1;
+        if (20 * gs <= smem_optin - 5 * 1024) return 3;  // 5 CTAs/SM, <=96 regs
+        return 0;
     }
 
     int ensure_capacity(int64_t n_new_total, int64_t upper_rows_total) {
@@ -571,11 +577,13 @@ int bh_index_train(bh_index* h, int64_t, const float*) {
 
 int bh_index_add(bh_index* h, int64_t n, const float* x) {
     if (!h) return fail("null index");
+    std::lock_guard<std::mutex> lk(h->mu);
     return add_impl(h, n, x, nullptr, nullptr);
 }
 
 int bh_index_add_ex(bh_index* h, int64_t n, const float* x, const int32_t* levels, const int32_t* order) {
     if (!h) return fail("null index");
+    std::lock_guard<std::mutex> lk(h->mu);
     return add_impl(h, n, x, levels, order);
 }
 
@@ -586,6 +594,7 @@ int bh_index_search_device(const bh_index* h, int64_t n, const float* x, int64_t
     if (n == 0) return 0;
     if (h->ntotal == 0) return fail("search_device: empty index");
     if (n > INT32_MAX) return fail("search_device: n too large for one call");
+    std::lock_guard<std::mutex> lk(h->mu);
     BH_CUDA(cudaSetDevice(h->device));
     return search_device_impl(h, n, x, k, distances, labels, params ? params->stats : nullptr, params);
 }
@@ -596,6 +605,7 @@ int bh_index_search(const bh_index* h, int64_t n, const float* x, int64_t k, flo
     if (n < 0 || k <= 0) return fail("search: need n >= 0 and k > 0");
     if (n == 0) return 0;
     if (!x || !distances || !labels) return fail("search: null buffer");
+    std::lock_guard<std::mutex> lk(h->mu);
     if (h->ntotal == 0) {  // HNSW::search returns at once on an empty graph: heaps stay (FLT_MAX,-1)
         const float pad = h->metric == BH_METRIC_L2 ? FLT_MAX : -FLT_MAX;
         for (int64_t i = 0; i < n * k; i++) {
