@@ -17,7 +17,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200_hnsw.h")
 class SearchParams(C.Structure):
     _fields_ = [("efSearch", C.c_int32), ("check_relative_distance", C.c_int32),
                 ("warps_per_query", C.c_int32), ("hash_bits", C.c_int32),
-                ("stats", C.c_void_p)]
+                ("stats", C.c_void_p), ("sel_bitmap", C.c_void_p), ("sel_bitmap_bytes", C.c_int64)]
 
 
 class BuildParams(C.Structure):

@@ -33,19 +33,20 @@ struct GroupSmem {
     int32_t* cand_id;              // [deg] ids to score this hop; reused for merge positions
     unsigned long long* cand_key;  // [deg]
     unsigned long long* acc_key;   // [deg]
-    int32_t* ctrl;  // [0]=n_new / stop, [1]=lsize, [3]=work index
+    int32_t* ctrl;  // [0]=n_new / stop, [1]=lsize, [2]=rsize, [3]=work index
     uint32_t* hash;
+    unsigned long long* rlist;     // [rk] selector-filtered result list (rk = k with an IDSelector, else 0)
 };
 
 __host__ __device__ inline size_t round16(size_t x) { return (x + 15) & ~size_t(15); }
 
-// deg = longest adjacency row (2M)
-__host__ __device__ inline size_t group_smem_bytes(int d, int ef, int hash_slots, int deg) {
+// deg = longest adjacency row (2M); rk = result-list entries (k when an IDSelector is set, else 0)
+__host__ __device__ inline size_t group_smem_bytes(int d, int ef, int hash_slots, int deg, int rk = 0) {
     return 16 + round16((size_t)d * 4) + round16((size_t)ef * 8) + round16((size_t)deg * 4) +
-           2 * round16((size_t)deg * 8) + 32 + (size_t)hash_slots * 4;
+           2 * round16((size_t)deg * 8) + 32 + (size_t)hash_slots * 4 + round16((size_t)rk * 8);
 }
 
-__device__ inline GroupSmem carve_group_smem(unsigned char* p, int d, int ef, int hash_slots, int deg) {
+__device__ inline GroupSmem carve_group_smem(unsigned char* p, int d, int ef, int hash_slots, int deg, int rk = 0) {
     GroupSmem s;
     s.mbar = reinterpret_cast<uint64_t*>(p);
     p += 16;
@@ -62,6 +63,8 @@ __device__ inline GroupSmem carve_group_smem(unsigned char* p, int d, int ef, in
     s.ctrl = reinterpret_cast<int32_t*>(p);
     p += 32;
     s.hash = reinterpret_cast<uint32_t*>(p);
+    p += (size_t)hash_slots * 4;
+    s.rlist = rk ? reinterpret_cast<unsigned long long*>(p) : nullptr;
     return s;
 }
 
@@ -299,9 +302,11 @@ struct Beam {
     //          (faiss count_below test; INT_MAX disables)
     // max_steps  faiss `!check_relative_distance && nstep > efSearch` (INT_MAX disables)
     // On return ctrl[1] = list size.
+    // sel/rk: faiss IDSelectorBitmap and the k of the selector-filtered result list (nullptr/0: none).
+    //          The selector decides only what enters the RESULT list; traversal is unchanged.
     __device__ void run(int level, int ef, int ef_stop, int max_steps, int hash_bits, uint32_t start_id,
-                        float start_d, BeamStats& st) const {
-        int lsize = 0, cursor = 0, hcount = 0, nstep = 0;
+                        float start_d, BeamStats& st, const uint8_t* sel = nullptr, int rk = 0) const {
+        int lsize = 0, cursor = 0, hcount = 0, nstep = 0, rsize = 0, rcursor = 0;
         const int hlimit = (3 << hash_bits) >> 2;  // reset above 75 % load
         if (wig == 0) {
             hash_clear(hash_bits);
@@ -311,6 +316,10 @@ struct Beam {
             }
             lsize = 1;
             hcount = 1;
+            if (sel && ((sel[start_id >> 3] >> (start_id & 7)) & 1)) {
+                if (lane == 0) s.rlist[0] = pack_key(start_d, start_id);
+                rsize = 1;
+            }
             __syncwarp();
         }
         for (;;) {
@@ -339,6 +348,14 @@ struct Beam {
                         hash_clear(hash_bits);
                         for (int i = lane; i < lsize; i += 32) hash_test_and_set(key_id(L[i]), hash_bits);
                         hcount = lsize;
+                        if (sel) {  // results outside the list must stay "visited" too, or they could re-enter twice
+                            int extra = 0;
+                            for (int i = lane; i < rsize; i += 32)
+                                extra += hash_test_and_set(key_id(s.rlist[i]), hash_bits) ? 1 : 0;
+#pragma unroll
+                            for (int off = 16; off >= 1; off >>= 1) extra += __shfl_xor_sync(0xffffffffu, extra, off);
+                            hcount += extra;
+                        }
                         __syncwarp();
                     }
                     n_new = 0;
@@ -362,10 +379,16 @@ struct Beam {
             if (n_new < 0) break;
             compute_dists(n_new);
             group_sync();
-            if (wig == 0 && n_new > 0) merge(n_new, ef, lsize, cursor);
+            if (wig == 0 && n_new > 0) {
+                merge(s.list, n_new, ef, lsize, cursor, nullptr);
+                if (sel) merge(s.rlist, n_new, rk, rsize, rcursor, sel);
+            }
         }
         if (wig == 0) {
-            if (lane == 0) s.ctrl[1] = lsize;
+            if (lane == 0) {
+                s.ctrl[1] = lsize;
+                s.ctrl[2] = rsize;
+            }
             __syncwarp();
         }
     }
@@ -377,8 +400,9 @@ struct Beam {
     // from its tail in 32-entry chunks (read chunk, sync, write chunk: a chunk's writes land at or
     // above its own base, i.e. only on slots already vacated); entries below the smallest
     // insertion point are not touched at all; accepted keys drop into the holes at the end.
-    __device__ __forceinline__ void merge(int n_new, int ef, int& lsize, int& cursor) const {
-        unsigned long long* L = s.list;
+    // `L` is the candidate list (capacity ef) or, with `sel`, the selector-filtered result list.
+    __device__ __forceinline__ void merge(unsigned long long* L, int n_new, int ef, int& lsize, int& cursor,
+                                          const uint8_t* sel) const {
         const bool full = lsize == ef;
         const unsigned long long thr = full ? key_clean(L[ef - 1]) : ~0ull;
         int n_acc = 0;
@@ -389,6 +413,10 @@ struct Beam {
             if (j < n_new) {
                 kj = s.cand_key[j];
                 ok = kj < thr;
+                if (ok && sel) {
+                    const uint32_t id = key_id(kj);
+                    ok = (__ldg(sel + (id >> 3)) >> (id & 7)) & 1;
+                }
             }
             const unsigned bal = __ballot_sync(0xffffffffu, ok);
             if (ok) s.acc_key[n_acc + __popc(bal & ((1u << lane) - 1u))] = kj;

@@ -21,8 +21,9 @@ __global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, Bea
     const int grp = warp / W;
     const int wig = warp % W;
     const int hash_slots = 1 << t.hash_bits;
-    const size_t gbytes = group_smem_bytes(g.d, t.ef, hash_slots, g.deg0);
-    const GroupSmem s = carve_group_smem(smem_raw + grp * gbytes, g.d, t.ef, hash_slots, g.deg0);
+    const int rk = t.sel ? t.k : 0;
+    const size_t gbytes = group_smem_bytes(g.d, t.ef, hash_slots, g.deg0, rk);
+    const GroupSmem s = carve_group_smem(smem_raw + grp * gbytes, g.d, t.ef, hash_slots, g.deg0, rk);
     Beam<TEAM, CPL, W, R> beam(g, s, wig, lane, 1 + grp);
 
     if (wig == 0 && lane == 0) {
@@ -63,11 +64,11 @@ __global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, Bea
         uint32_t cur_id = 0;
         float cur_d = 0.f;
         beam.descend(stop_level, cur_id, cur_d, st);
-        beam.run(level, t.ef, t.ef_stop, t.max_steps, t.hash_bits, cur_id, cur_d, st);
+        beam.run(level, t.ef, t.ef_stop, t.max_steps, t.hash_bits, cur_id, cur_d, st, t.sel, rk);
 
         if (wig == 0) {
-            const int lsize = s.ctrl[1];
-            const unsigned long long* L = s.list;
+            const int lsize = t.sel ? s.ctrl[2] : s.ctrl[1];
+            const unsigned long long* L = t.sel ? s.rlist : s.list;
             if (t.items) {
                 unsigned long long* out = t.out_lists + (size_t)wi * t.ef;
                 for (int i = lane; i < lsize; i += 32) out[i] = key_clean(L[i]);
@@ -102,7 +103,7 @@ template <int TEAM, int CPL, int W, int R, int G, int MINB>
 cudaError_t launch_one(const GraphView& g, const BeamTask& t, int num_sms, cudaStream_t stream,
                        int* grid_out) {
     auto kern = beam_kernel<TEAM, CPL, W, R, G, MINB>;
-    const size_t smem = (size_t)G * group_smem_bytes(g.d, t.ef, 1 << t.hash_bits, g.deg0);
+    const size_t smem = (size_t)G * group_smem_bytes(g.d, t.ef, 1 << t.hash_bits, g.deg0, t.sel ? t.k : 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
@@ -146,7 +147,9 @@ int team_for_dim(int d) {
     return 32;
 }
 
-size_t beam_group_smem(int d, int ef, int hash_bits, int deg) { return group_smem_bytes(d, ef, 1 << hash_bits, deg); }
+size_t beam_group_smem(int d, int ef, int hash_bits, int deg, int rk) {
+    return group_smem_bytes(d, ef, 1 << hash_bits, deg, rk);
+}
 
 cudaError_t launch_beam(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
                         cudaStream_t stream, int* grid_out) {

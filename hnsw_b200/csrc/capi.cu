@@ -106,6 +106,7 @@ struct bh_index {
     mutable DevBuf<float> q_d, D_d;
     mutable DevBuf<int64_t> I_d;
     mutable DevBuf<int32_t> stats_d;
+    mutable DevBuf<uint8_t> sel_d;
     mutable float last_search_ms = 0.f;
     float last_build_ms = 0.f;
     // build scratch
@@ -225,6 +226,7 @@ struct bh_index {
     void free_all() {
         nver0.release(); nverU.release();
         vecs.release(); nbr0.release(); upper_base_d.release(); upper_nbr.release(); slot_head.release();
+        sel_d.release();
         counter.release(); q_d.release(); D_d.release(); I_d.release(); stats_d.release();
         items_d.release(); cand_lists.release(); cand_counts.release();
         e_slot.release(); e_src.release(); e_dst.release(); e_level.release(); e_next.release(); e_dist.release();
@@ -234,17 +236,23 @@ struct bh_index {
 namespace {
 
 int search_device_impl(const bh_index* h, int64_t n, const float* xq_d, int64_t k, float* D_d,
-                       int64_t* I_d, int32_t* stats_d, const bh_search_params* params) {
+                       int64_t* I_d, int32_t* stats_d, const bh_search_params* params,
+                       const uint8_t* sel_dev = nullptr) {
     const int efS = (params && params->efSearch > 0) ? params->efSearch : h->efSearch;
     bool crd = h->check_relative_distance;
     if (params && params->check_relative_distance == 1) crd = true;
     if (params && params->check_relative_distance == 2) crd = false;
     const int ef = (int)std::max<int64_t>(efS, k);
     if (ef > 4096) return fail("max(efSearch, k) > 4096 is not supported");
-    const int hb = h->auto_hash_bits(ef, params ? params->hash_bits : 0);
-    const int W = h->auto_warps(ef, hb, params ? params->warps_per_query : 0, n);
-    const int G = W >= 4 ? 1 : 4 / W;
-    if (G * bh::beam_group_smem(h->d, ef, hb, h->deg0()) > h->smem_optin)
+    const int rk = sel_dev ? (int)k : 0;  // selector-filtered result list lives beside the candidate list
+    const int hb = h->auto_hash_bits(ef + rk, params ? params->hash_bits : 0);
+    int W = h->auto_warps(ef + rk, hb, params ? params->warps_per_query : 0, n);
+    int G = W >= 4 ? 1 : 4 / W;
+    while (G * bh::beam_group_smem(h->d, ef, hb, h->deg0(), rk) > h->smem_optin && W < 4) {
+        W *= 2;
+        G = W >= 4 ? 1 : 4 / W;
+    }
+    if (G * bh::beam_group_smem(h->d, ef, hb, h->deg0(), rk) > h->smem_optin)
         return fail("efSearch/hash_bits need more shared memory than one SM has");
     bh::BeamTask t{};
     t.queries = xq_d;
@@ -258,9 +266,10 @@ int search_device_impl(const bh_index* h, int64_t n, const float* xq_d, int64_t 
     t.max_steps = crd ? INT_MAX : efS;
     t.hash_bits = hb;
     t.stats = stats_d;
+    t.sel = sel_dev;
     t.counter = h->counter.p;
     BH_CUDA(cudaMemsetAsync(h->counter.p, 0, sizeof(int), h->stream));
-    BH_CUDA(bh::launch_beam(h->view(), t, W, h->beam_variant(ef, hb), h->num_sms, h->stream, nullptr));
+    BH_CUDA(bh::launch_beam(h->view(), t, W, h->beam_variant(ef + rk, hb), h->num_sms, h->stream, nullptr));
     bh::count_launch();
     return 0;
 }
@@ -596,7 +605,10 @@ int bh_index_search_device(const bh_index* h, int64_t n, const float* x, int64_t
     if (n > INT32_MAX) return fail("search_device: n too large for one call");
     std::lock_guard<std::mutex> lk(h->mu);
     BH_CUDA(cudaSetDevice(h->device));
-    return search_device_impl(h, n, x, k, distances, labels, params ? params->stats : nullptr, params);
+    if (params && params->sel_bitmap && params->sel_bitmap_bytes < (h->ntotal + 7) / 8)
+        return fail("search: sel_bitmap is smaller than (ntotal + 7) / 8 bytes");
+    return search_device_impl(h, n, x, k, distances, labels, params ? params->stats : nullptr, params,
+                              params ? params->sel_bitmap : nullptr);
 }
 
 int bh_index_search(const bh_index* h, int64_t n, const float* x, int64_t k, float* distances,
@@ -615,6 +627,14 @@ int bh_index_search(const bh_index* h, int64_t n, const float* x, int64_t k, flo
         return 0;
     }
     BH_CUDA(cudaSetDevice(h->device));
+    const uint8_t* sel_dev = nullptr;
+    if (params && params->sel_bitmap) {
+        const int64_t need = (h->ntotal + 7) / 8;
+        if (params->sel_bitmap_bytes < need) return fail("search: sel_bitmap is smaller than (ntotal + 7) / 8 bytes");
+        BH_CUDA(h->sel_d.reserve((size_t)need, h->stream));
+        BH_CUDA(cudaMemcpyAsync(h->sel_d.p, params->sel_bitmap, (size_t)need, cudaMemcpyHostToDevice, h->stream));
+        sel_dev = h->sel_d.p;
+    }
     // Zero-copy path: when the caller's buffers are page-locked (cudaHostAlloc / cudaHostRegister,
     // e.g. torch pinned tensors) they are device-addressable under UVA, so the kernel reads each
     // query straight from host memory with its TMA bulk copy and writes the k results back over
@@ -633,7 +653,7 @@ int bh_index_search(const bh_index* h, int64_t n, const float* x, int64_t k, flo
         void* ld = dev_ptr(labels);
         if (xd && dd && ld) {
             BH_CUDA(cudaEventRecord(h->ev0, h->stream));
-            if (int rc = search_device_impl(h, n, (const float*)xd, k, (float*)dd, (int64_t*)ld, nullptr, params))
+            if (int rc = search_device_impl(h, n, (const float*)xd, k, (float*)dd, (int64_t*)ld, nullptr, params, sel_dev))
                 return rc;
             BH_CUDA(cudaEventRecord(h->ev1, h->stream));
             BH_CUDA(cudaStreamSynchronize(h->stream));
@@ -655,7 +675,7 @@ int bh_index_search(const bh_index* h, int64_t n, const float* x, int64_t k, flo
                                 cudaMemcpyHostToDevice, h->stream));
         BH_CUDA(cudaEventRecord(h->ev0, h->stream));
         if (int rc = search_device_impl(h, m, h->q_d.p, k, h->D_d.p, h->I_d.p,
-                                        stats_host ? h->stats_d.p : nullptr, params))
+                                        stats_host ? h->stats_d.p : nullptr, params, sel_dev))
             return rc;
         BH_CUDA(cudaEventRecord(h->ev1, h->stream));
         BH_CUDA(cudaMemcpyAsync(distances + (size_t)i0 * k, h->D_d.p, (size_t)m * k * sizeof(float),

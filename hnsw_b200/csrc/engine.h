@@ -26,11 +26,12 @@ struct BeamTask {
     int max_steps;  // nstep limit (INT_MAX = off)
     int hash_bits;
     int32_t* stats;  // device int32[n_items][4] or null
+    const uint8_t* sel;  // device IDSelectorBitmap over the shard's ids, or null (search mode only)
     int* counter;    // device work counter, zeroed before launch
 };
 
 int team_for_dim(int d);
-size_t beam_group_smem(int d, int ef, int hash_bits, int deg);
+size_t beam_group_smem(int d, int ef, int hash_bits, int deg, int rk = 0);
 cudaError_t launch_beam(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
                         cudaStream_t stream, int* grid_out);
 

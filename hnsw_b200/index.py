@@ -111,8 +111,11 @@ class IndexHNSWFlat:
                                               None if od is None else od.ctypes.data))
 
     def search(self, x, k: int, params: SearchParams | None = None, efSearch: int | None = None,
-               stats: bool = False, out=None, warps_per_query: int = 0, hash_bits: int = 0):
-        """faiss Index.search → (D, I). `out=(D, I)` reuses caller buffers (e.g. pinned)."""
+               stats: bool = False, out=None, warps_per_query: int = 0, hash_bits: int = 0,
+               sel_bitmap=None):
+        """faiss Index.search → (D, I). `out=(D, I)` reuses caller buffers (e.g. pinned).
+        `sel_bitmap`: uint8 array in faiss IDSelectorBitmap layout (np.packbits(mask, bitorder="little"));
+        only ids whose bit is set can be returned (SearchParametersHNSW.sel semantics)."""
         x = self._as_f32(x)
         nq = x.shape[0]
         if out is None:
@@ -122,9 +125,13 @@ class IndexHNSWFlat:
             D, I = out
         st = np.zeros((nq, 4), np.int32) if stats else None
         if params is None:
-            params = SearchParams(int(efSearch or 0), 0, int(warps_per_query), int(hash_bits), None)
+            params = SearchParams(int(efSearch or 0), 0, int(warps_per_query), int(hash_bits), None, None, 0)
         if st is not None:
             params.stats = st.ctypes.data
+        if sel_bitmap is not None:
+            sel_bitmap = np.ascontiguousarray(sel_bitmap, np.uint8)
+            params.sel_bitmap = sel_bitmap.ctypes.data
+            params.sel_bitmap_bytes = sel_bitmap.size
         _lib.check(_lib.lib().bh_index_search(self._h, nq, x.ctypes.data, int(k), D.ctypes.data,
                                               I.ctypes.data, C.byref(params)))
         return (D, I, st) if stats else (D, I)
@@ -133,7 +140,7 @@ class IndexHNSWFlat:
                       efSearch: int = 0, stats_ptr: int = 0, warps_per_query: int = 0,
                       hash_bits: int = 0):
         """Enqueue a search on device buffers (raw pointers); no host sync."""
-        p = SearchParams(int(efSearch), 0, int(warps_per_query), int(hash_bits), stats_ptr or None)
+        p = SearchParams(int(efSearch), 0, int(warps_per_query), int(hash_bits), stats_ptr or None, None, 0)
         _lib.check(_lib.lib().bh_index_search_device(self._h, int(nq), xq_ptr, int(k), D_ptr, I_ptr,
                                                      C.byref(p)))
 

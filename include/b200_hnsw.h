@@ -37,6 +37,11 @@ typedef struct bh_search_params {
     int32_t hash_bits;               /* 0: auto; log2 of the visited-hash slots per query */
     int32_t* stats;                  /* optional int32[n][4]: {ndis L0, nhops L0, ndis upper,
                                         nhops upper}; host ptr (device ptr for *_device) */
+    const uint8_t* sel_bitmap;       /* optional faiss::IDSelectorBitmap (SearchParametersHNSW::sel):
+                                        id i may be returned iff bit (i & 7) of byte (i >> 3) is set.
+                                        As in faiss it filters results only, not the traversal.
+                                        host ptr (device ptr for *_device); NULL = no selector */
+    int64_t sel_bitmap_bytes;        /* size of sel_bitmap, must be >= (ntotal + 7) / 8 */
 } bh_search_params;
 
 /* Build-time knobs (no faiss equivalent: faiss's concurrency is the OpenMP thread count). */

@@ -22,7 +22,7 @@
 //   team == 0 : "native" — 16 independent partial sums, auto-vectorised (AVX-512 here);
 //               this is the mode the CPU baseline is timed in.
 //   team == T : emulates, bit for bit, the summation order of the CUDA kernels
-//               (hnsw_b200/csrc/distance.cuh): lane j of a T-lane team owns the float4
+//               (hnsw_b200/csrc/beam.cuh, build_kernels.cu): lane j of a T-lane team owns the float4
 //               chunks j, j+T, j+2T…, accumulates them with one fmaf chain, then the
 //               team is reduced by an xor-butterfly. Used by the parity tests so that
 //               oracle and GPU traverse the same graph along the same path.
@@ -341,17 +341,23 @@ void greedy_update_nearest(const Oracle& h, DistanceComputer& qdis, int level,
 }
 
 // A.6 — search_from_candidates (bounded queue; the default branch)
+// `sel` (may be null) is faiss's IDSelectorBitmap: id i is a member iff bit (i & 7) of byte i >> 3 is
+// set. As in faiss the selector filters what enters the RESULT heap only; traversal is unchanged.
+inline bool is_member(const uint8_t* sel, idx_t id) { return !sel || ((sel[id >> 3] >> (id & 7)) & 1); }
+
 int search_from_candidates(const Oracle& h, DistanceComputer& qdis, int k, idx_t* I, float* D,
                            MinimaxHeap& candidates, VisitedTable& vt, int level, int efSearch,
-                           bool do_dis_check, QueryStats* st) {
+                           bool do_dis_check, QueryStats* st, const uint8_t* sel = nullptr) {
     int nres = 0;
     for (int i = 0; i < candidates.k; i++) {
         idx_t v1 = candidates.ids[i];
         float dd = candidates.dis[i];
-        if (nres < k) {
-            maxheap_push<idx_t>(++nres, D, I, dd, v1);
-        } else if (dd < D[0]) {
-            maxheap_replace_top<idx_t>(nres, D, I, dd, v1);
+        if (is_member(sel, v1)) {
+            if (nres < k) {
+                maxheap_push<idx_t>(++nres, D, I, dd, v1);
+            } else if (dd < D[0]) {
+                maxheap_replace_top<idx_t>(nres, D, I, dd, v1);
+            }
         }
         vt.set((int)v1);
     }
@@ -372,10 +378,12 @@ int search_from_candidates(const Oracle& h, DistanceComputer& qdis, int k, idx_t
             vt.set(v1);
             if (st) st->ndis0++;
             float dd = qdis(v1);
-            if (nres < k) {
-                maxheap_push<idx_t>(++nres, D, I, dd, (idx_t)v1);
-            } else if (dd < D[0]) {
-                maxheap_replace_top<idx_t>(nres, D, I, dd, (idx_t)v1);
+            if (is_member(sel, v1)) {
+                if (nres < k) {
+                    maxheap_push<idx_t>(++nres, D, I, dd, (idx_t)v1);
+                } else if (dd < D[0]) {
+                    maxheap_replace_top<idx_t>(nres, D, I, dd, (idx_t)v1);
+                }
             }
             candidates.push(v1, dd);
         }
@@ -387,7 +395,7 @@ int search_from_candidates(const Oracle& h, DistanceComputer& qdis, int k, idx_t
 
 // A.5 — HNSW::search (upper_beam == 1, search_bounded_queue == true only)
 int hnsw_search(const Oracle& h, DistanceComputer& qdis, int k, idx_t* I, float* D,
-                VisitedTable& vt, int efSearch, QueryStats* st) {
+                VisitedTable& vt, int efSearch, QueryStats* st, const uint8_t* sel = nullptr) {
     if (h.entry_point == -1) return 0;
     storage_idx_t nearest = h.entry_point;
     float d_nearest = qdis(nearest);
@@ -397,7 +405,7 @@ int hnsw_search(const Oracle& h, DistanceComputer& qdis, int k, idx_t* I, float*
     MinimaxHeap candidates(ef);
     candidates.push(nearest, d_nearest);
     int nres = search_from_candidates(h, qdis, k, I, D, candidates, vt, 0, efSearch,
-                                      h.check_relative_distance, st);
+                                      h.check_relative_distance, st, sel);
     vt.advance();
     return nres;
 }
@@ -671,8 +679,16 @@ void orc_peek_levels(void* p, int64_t n, int* levels_out) {
 // IndexHNSW::search: per query heapify → HNSW::search → reorder ascending;
 // IP distances are negated back at the end. stats (may be null) is int32[nq][4] =
 // {ndis level0, nhops level0, ndis upper, nhops upper}.
+int orc_search_sel(void* p, int64_t nq, const float* xq, int64_t k, float* D, int64_t* I,
+                   int ef_search, int nthreads, int32_t* stats, const uint8_t* sel);
+
 int orc_search(void* p, int64_t nq, const float* xq, int64_t k, float* D, int64_t* I,
                int ef_search /*<=0: index default*/, int nthreads, int32_t* stats) {
+    return orc_search_sel(p, nq, xq, k, D, I, ef_search, nthreads, stats, nullptr);
+}
+
+int orc_search_sel(void* p, int64_t nq, const float* xq, int64_t k, float* D, int64_t* I,
+                   int ef_search, int nthreads, int32_t* stats, const uint8_t* sel) {
     Oracle* o = static_cast<Oracle*>(p);
     if (k <= 0) return 1;
     const int ef = ef_search > 0 ? ef_search : o->efSearch;
@@ -690,7 +706,7 @@ int orc_search(void* p, int64_t nq, const float* xq, int64_t k, float* D, int64_
                 idxi[j] = -1;
             }
             QueryStats st;
-            int nres = hnsw_search(*o, dis, (int)k, idxi, simi, vt, ef, &st);
+            int nres = hnsw_search(*o, dis, (int)k, idxi, simi, vt, ef, &st, sel);
             // maxheap_reorder: valid entries ascending, then (FLT_MAX,-1) padding
             for (int m = nres; m > 1; m--) {
                 float v = simi[0];

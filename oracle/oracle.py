@@ -69,6 +69,9 @@ def _load(path: str | None = None) -> C.CDLL:
     L.orc_search.argtypes = [C.c_void_p, C.c_int64, _f32p, C.c_int64, _f32p, _i64p, C.c_int,
                              C.c_int, C.c_void_p]
     L.orc_search.restype = C.c_int
+    L.orc_search_sel.argtypes = [C.c_void_p, C.c_int64, _f32p, C.c_int64, _f32p, _i64p, C.c_int,
+                                 C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_search_sel.restype = C.c_int
     L.orc_export_graph.argtypes = [C.c_void_p, _i32p, _u64p, _i32p]
     L.orc_import.argtypes = [C.c_void_p, C.c_int64, _f32p, _i32p, _i32p, C.c_int64, C.c_int, C.c_int]
     L.orc_import.restype = C.c_int
@@ -156,14 +159,17 @@ class OracleHNSWFlat:
         self._L.orc_peek_levels(self._h, n, out)
         return out
 
-    def search(self, xq: np.ndarray, k: int, efSearch: int | None = None, stats: bool = False):
+    def search(self, xq: np.ndarray, k: int, efSearch: int | None = None, stats: bool = False,
+               sel_bitmap: np.ndarray | None = None):
         xq = np.ascontiguousarray(xq, dtype=np.float32)
         nq = xq.shape[0]
         D = np.empty((nq, k), np.float32)
         I = np.empty((nq, k), np.int64)
         st = np.zeros((nq, 4), np.int32) if stats else None
-        rc = self._L.orc_search(self._h, nq, xq, k, D, I, int(efSearch or 0), int(self.threads),
-                                st.ctypes.data if st is not None else None)
+        sel = None if sel_bitmap is None else np.ascontiguousarray(sel_bitmap, np.uint8)
+        rc = self._L.orc_search_sel(self._h, nq, xq, k, D, I, int(efSearch or 0), int(self.threads),
+                                    st.ctypes.data if st is not None else None,
+                                    sel.ctypes.data if sel is not None else None)
         if rc:
             raise RuntimeError(f"orc_search rc={rc}")
         return (D, I, st) if stats else (D, I)

@@ -232,3 +232,21 @@ def test_baseline_config0_plumbing(oracle_mod):
     r_cpu = oracle_mod.recall_at_k(Io, gt)
     r_gpu = oracle_mod.recall_at_k(g.search(xq, k, efSearch=ef)[1], gt)
     assert r_cpu > 0.9 and r_gpu >= r_cpu - 0.005, (r_cpu, r_gpu)
+
+
+@pytest.mark.parametrize("frac", [0.5, 0.1, 0.01])
+def test_id_selector_bitmap_matches_oracle(small_l2, frac):
+    """SearchParametersHNSW.sel (IDSelectorBitmap): filters the results, not the traversal."""
+    o = small_l2["oracle"]
+    idx = _gpu_from_oracle(o, small_l2["xb"], 16)
+    member = np.random.RandomState(int(frac * 1000)).rand(4000) < frac
+    bm = np.packbits(member, bitorder="little")
+    for ef, k, hb in ((64, 10, 13), (32, 40, 13), (64, 10, 0), (128, 10, 9)):
+        Do, Io, So = o.search(small_l2["xq"], k, ef, stats=True, sel_bitmap=bm)
+        D, I, S = idx.search(small_l2["xq"], k, efSearch=ef, stats=True, hash_bits=hb, sel_bitmap=bm)
+        assert np.array_equal(I, Io) and np.array_equal(D, Do), (ef, k, hb)
+        assert member[I[I >= 0]].all()
+        if hb == 13:
+            assert np.array_equal(S, So)
+    with pytest.raises(RuntimeError):
+        idx.search(small_l2["xq"], 10, sel_bitmap=bm[:100])          # bitmap too small
