@@ -23,7 +23,19 @@ namespace bh {
 
 struct BeamStats {
     int ndis0 = 0, nhops0 = 0, ndis_up = 0, nhops_up = 0;
+#ifdef BH_PHASE_TIMING  // debug builds only: SM cycles per phase, summed over the query's hops
+    long long t_pop = 0, t_row = 0, t_hash = 0, t_gather = 0, t_merge = 0, t_reset = 0, t_probe = 0;
+    int n_reset = 0;
+#endif
 };
+
+#ifdef BH_PHASE_TIMING
+#define BH_T(var) const long long var = clock64()
+#define BH_ACC(field, a, b) st.field += (b) - (a)
+#else
+#define BH_T(var)
+#define BH_ACC(field, a, b)
+#endif
 
 // Per-group shared memory carve-up. Host and device must agree: see group_smem_bytes().
 struct GroupSmem {
@@ -207,19 +219,26 @@ struct Beam {
     }
 
     // ---- visited hash (leader warp) --------------------------------------------
+    // The table is read as buckets of four slots (one 128-bit shared load per probe step): a step
+    // answers "already visited" for four slots at once and names the first free slot, which is then
+    // claimed with one CAS (re-reading the same bucket if another lane took it first). Buckets fill
+    // front to back and nothing is ever deleted between clears, so a lookup moves to the next bucket
+    // only when its bucket has no free slot.
     __device__ __forceinline__ bool hash_test_and_set(uint32_t id, int bits) const {
-        const uint32_t mask = (1u << bits) - 1u;
-        uint32_t h = hash_id(id, bits);
-        volatile uint32_t* tab = s.hash;
+        const uint32_t bmask = (1u << (bits - 2)) - 1u;
+        uint32_t b = hash_id(id, bits - 2);
         for (;;) {
-            const uint32_t cur = tab[h];       // plain probe first: a CAS only on an empty slot
-            if (cur == id) return false;       // already visited
-            if (cur == kEmpty) {
-                const uint32_t old = atomicCAS(s.hash + h, kEmpty, id);
-                if (old == kEmpty) return true;  // newly inserted
-                if (old == id) return false;
+            const uint4 v = lds128_volatile(s.hash + 4 * b);
+            if (v.x == id || v.y == id || v.z == id || v.w == id) return false;  // already visited
+            const int j = v.x == kEmpty ? 0 : (v.y == kEmpty ? 1 : (v.z == kEmpty ? 2 : (v.w == kEmpty ? 3 : -1)));
+            if (j < 0) {
+                b = (b + 1) & bmask;
+                continue;
             }
-            h = (h + 1) & mask;
+            const uint32_t old = atomicCAS(s.hash + 4 * b + j, kEmpty, id);
+            if (old == kEmpty) return true;   // newly inserted
+            if (old == id) return false;      // a twin lane inserted the same id first
+            // slot taken by another lane meanwhile: look at the same bucket again
         }
     }
     __device__ __forceinline__ void hash_clear(int bits) const {
@@ -325,6 +344,7 @@ struct Beam {
         for (;;) {
             if (wig == 0) {
                 // -- pop_min: first unexpanded entry of the sorted list
+                BH_T(t0);
                 int pos = -1;
                 const unsigned long long* L = s.list;
                 for (int b = cursor & ~31; b < lsize; b += 32) {
@@ -343,7 +363,12 @@ struct Beam {
                     if (lane == 0) s.list[pos] = L[pos] | kExpanded;
                     cursor = pos + 1;
                     int ids[kMaxIdsPerLane];
+                    BH_T(t1);
+                    BH_ACC(t_pop, t0, t1);
                     load_row((int)v0, level, ids);
+                    BH_T(t2);
+                    BH_ACC(t_row, t1, t2);
+                    BH_T(t2a);
                     if (hcount + (level == 0 ? g.deg0 : g.degU) > hlimit) {  // forget-and-reseed (see header)
                         hash_clear(hash_bits);
                         for (int i = lane; i < lsize; i += 32) hash_test_and_set(key_id(L[i]), hash_bits);
@@ -358,6 +383,8 @@ struct Beam {
                         }
                         __syncwarp();
                     }
+                    BH_T(t2b);
+                    BH_ACC(t_reset, t2a, t2b);
                     n_new = 0;
 #pragma unroll
                     for (int i = 0; i < kMaxIdsPerLane; i++) {
@@ -370,6 +397,9 @@ struct Beam {
                     st.ndis0 += n_new;
                     st.nhops0 += 1;
                     nstep++;
+                    BH_T(t3);
+                    BH_ACC(t_hash, t2, t3);
+                    BH_ACC(t_probe, t2b, t3);
                 }
                 if (lane == 0) s.ctrl[0] = n_new;
                 __syncwarp();
@@ -377,12 +407,17 @@ struct Beam {
             group_sync();
             const int n_new = s.ctrl[0];
             if (n_new < 0) break;
+            BH_T(t4);
             compute_dists(n_new);
             group_sync();
+            BH_T(t5);
+            BH_ACC(t_gather, t4, t5);
             if (wig == 0 && n_new > 0) {
                 merge(s.list, n_new, ef, lsize, cursor, nullptr);
                 if (sel) merge(s.rlist, n_new, rk, rsize, rcursor, sel);
             }
+            BH_T(t6);
+            BH_ACC(t_merge, t5, t6);
         }
         if (wig == 0) {
             if (lane == 0) {

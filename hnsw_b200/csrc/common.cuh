@@ -90,6 +90,16 @@ __device__ __forceinline__ void bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// One volatile 128-bit shared-memory load (a 4-slot hash bucket).
+__device__ __forceinline__ uint4 lds128_volatile(const void* smem_ptr) {
+    uint4 v;
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(smem_u32(smem_ptr))
+                 : "memory");
+    return v;
+}
+
 // 128-bit read-only gather load that does not allocate in L1 (rows are not reused by the SM).
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     float4 r;
