@@ -461,7 +461,6 @@ struct Beam {
         __syncwarp();
         int* acc_pos = s.cand_id;  // free again: the hop's ids have been scored
         int minpos = ef;
-        unsigned long long minacc = ~0ull;
         for (int a = lane; a < n_acc; a += 32) {
             const unsigned long long ka = s.acc_key[a];
             int ra = 0;
@@ -474,16 +473,10 @@ struct Beam {
             const int pos = ra + lo;
             acc_pos[a] = pos;
             minpos = pos < minpos ? pos : minpos;
-            minacc = ka < minacc ? ka : minacc;
         }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            const int om = __shfl_xor_sync(0xffffffffu, minpos, off);
-            minpos = om < minpos ? om : minpos;
-            const unsigned long long oa = __shfl_xor_sync(0xffffffffu, minacc, off);
-            minacc = oa < minacc ? oa : minacc;
-        }
+        minpos = __reduce_min_sync(0xffffffffu, minpos);  // REDUX: one instruction
         __syncwarp();
+        // entries before the first insertion point stay where they are (nothing accepted is below them)
         if (lsize > 0) {
             for (int b = (lsize - 1) & ~31; b >= (minpos & ~31); b -= 32) {
                 const int i = b + lane;
@@ -491,10 +484,11 @@ struct Beam {
                 int np = ef;
                 if (i < lsize) {
                     e = L[i];
-                    const unsigned long long ec = key_clean(e);
                     int cnt = 0;
-                    if (ec > minacc)
+                    if (i >= minpos) {
+                        const unsigned long long ec = key_clean(e);
                         for (int b2 = 0; b2 < n_acc; b2++) cnt += s.acc_key[b2] < ec;
+                    }
                     np = i + cnt;
                 }
                 __syncwarp();
