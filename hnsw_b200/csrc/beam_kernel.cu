@@ -148,12 +148,6 @@ cudaError_t launch_w(const GraphView& g, const BeamTask& t, int W, int variant, 
 
 }  // namespace
 
-int team_for_dim(int d) {
-    if (d <= 128) return 8;
-    if (d <= 256) return 16;
-    return 32;
-}
-
 size_t beam_group_smem(int d, int ef, int hash_bits, int deg, int rk) {
     return group_smem_bytes(d, ef, 1 << hash_bits, deg, rk);
 }

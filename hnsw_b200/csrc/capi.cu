@@ -116,7 +116,6 @@ struct bh_index {
     DevBuf<float> e_dist;
 
     int deg0() const { return 2 * M; }
-    int nb_neighbors(int level) const { return cum_nn[level + 1] - cum_nn[level]; }
 
     bh::GraphView view() const {
         bh::GraphView g;
@@ -384,7 +383,10 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     // -- batch schedule. A round inserts points concurrently against the graph as it stood at the
     //    start of the round (faiss's OpenMP build has the same blindness between the points its
     //    threads are inserting at one moment). Rounds are kept small relative to the graph.
-    const int max_batch = h->bp.max_batch > 0 ? h->bp.max_batch : 8192;
+    // auto: 8192 points per round, growing with the graph beyond 2M vertices (a round never exceeds
+    // 1/256 of the graph there), capped at 64k
+    const bool auto_batch = h->bp.max_batch <= 0;
+    const int max_batch = auto_batch ? 8192 : h->bp.max_batch;
     const int divisor = h->bp.batch_divisor > 0 ? h->bp.batch_divisor : 64;
     struct Round { int64_t item_begin, item_end; int new_entry, new_max_level; };
     std::vector<int4> items;
@@ -403,7 +405,9 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
             pos = 1;
         }
         while (pos < n) {
-            int64_t target = std::max<int64_t>(1, std::min<int64_t>(max_batch, in_graph / divisor));
+            int64_t cap = max_batch;
+            if (auto_batch) cap = std::min<int64_t>(65536, std::max<int64_t>(cap, in_graph / 256));
+            int64_t target = std::max<int64_t>(1, std::min<int64_t>(cap, in_graph / divisor));
             Round r{(int64_t)items.size(), 0, -1, -1};
             int64_t cnt = 0;
             while (pos < n && cnt < target) {
@@ -842,17 +846,13 @@ float bh_index_last_search_ms(const bh_index* h) { return h ? h->last_search_ms 
 int bh_merge_topk_device(int nshard, int64_t nq, int64_t k, int metric, const float* D_all,
                          const int64_t* I_all, const int64_t* id_offsets, float* D_out, int64_t* I_out,
                          void* stream) {
-    if (nshard < 1 || nshard > 64 || nq < 0 || k <= 0 || k > 4096) return fail("merge: bad shape");
+    if (nshard < 1 || nshard > bh::kMaxShards || nq < 0 || k <= 0 || k > 4096) return fail("merge: bad shape");
     if (!D_all || !I_all || !id_offsets || !D_out || !I_out) return fail("merge: null buffer");
-    cudaStream_t s = (cudaStream_t)stream;
-    int64_t* off_d = nullptr;
-    BH_CUDA(cudaMalloc(&off_d, nshard * sizeof(int64_t)));
-    cudaError_t e = cudaMemcpyAsync(off_d, id_offsets, nshard * sizeof(int64_t), cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess)
-        e = bh::launch_merge_topk(nshard, nq, (int)k, metric == BH_METRIC_L2, D_all, I_all, off_d, D_out, I_out, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    cudaFree(off_d);
-    if (e != cudaSuccess) return fail(std::string("merge: ") + cudaGetErrorString(e));
+    bh::ShardOffsets off{};
+    for (int i = 0; i < nshard; i++) off.v[i] = id_offsets[i];
+    // enqueued on `stream`, no allocation and no synchronisation: the caller's stream orders it
+    BH_CUDA(bh::launch_merge_topk(nshard, nq, (int)k, metric == BH_METRIC_L2, D_all, I_all, off, D_out, I_out,
+                                  (cudaStream_t)stream));
     return 0;
 }
 

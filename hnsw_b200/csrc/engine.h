@@ -30,7 +30,6 @@ struct BeamTask {
     int* counter;    // device work counter, zeroed before launch
 };
 
-int team_for_dim(int d);
 size_t beam_group_smem(int d, int ef, int hash_bits, int deg, int rk = 0);
 cudaError_t launch_beam(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
                         cudaStream_t stream, int* grid_out);
@@ -62,8 +61,12 @@ cudaError_t launch_select_and_link(const GraphView& g, const BuildBatch& b, int 
 cudaError_t launch_backlinks(const GraphView& g, const BuildBatch& b, int num_sms, cudaStream_t stream);
 
 // ---- sharded top-k merge (merge_kernel.cu) ---------------------------------------
+constexpr int kMaxShards = 64;
+struct ShardOffsets {  // passed by value in the kernel parameters: no allocation, copy or sync per merge
+    int64_t v[kMaxShards];
+};
 cudaError_t launch_merge_topk(int nshard, int64_t nq, int k, int is_l2, const float* D_all,
-                              const int64_t* I_all, const int64_t* id_offsets_dev, float* D_out,
+                              const int64_t* I_all, const ShardOffsets& id_offsets, float* D_out,
                               int64_t* I_out, cudaStream_t stream);
 
 void count_launch(int n = 1);

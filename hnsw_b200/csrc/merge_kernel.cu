@@ -14,7 +14,7 @@ namespace {
 __global__ void __launch_bounds__(128) merge_topk_kernel(int nshard, int64_t nq, int k, int is_l2,
                                                          const float* __restrict__ D_all,
                                                          const int64_t* __restrict__ I_all,
-                                                         const int64_t* __restrict__ id_off,
+                                                         const ShardOffsets id_off,
                                                          float* __restrict__ D_out,
                                                          int64_t* __restrict__ I_out) {
     const int lane = threadIdx.x & 31;
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(int nshard, int64_t nq,
             if (rank < k) {
                 const int64_t id = I_all[((size_t)s * nq + q) * k + i];
                 D_out[(size_t)q * k + rank] = v;
-                I_out[(size_t)q * k + rank] = id >= 0 ? id + id_off[s] : -1;
+                I_out[(size_t)q * k + rank] = id >= 0 ? id + id_off.v[s] : -1;
             }
         }
     }
@@ -52,14 +52,14 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(int nshard, int64_t nq,
 }  // namespace
 
 cudaError_t launch_merge_topk(int nshard, int64_t nq, int k, int is_l2, const float* D_all,
-                              const int64_t* I_all, const int64_t* id_offsets_dev, float* D_out,
+                              const int64_t* I_all, const ShardOffsets& id_offsets, float* D_out,
                               int64_t* I_out, cudaStream_t stream) {
     if (nq == 0) return cudaSuccess;
     const int wpb = 4;
     long long grid = (nq + wpb - 1) / wpb;
     if (grid > 148 * 16) grid = 148 * 16;
     merge_topk_kernel<<<(unsigned)grid, 32 * wpb, 0, stream>>>(nshard, nq, k, is_l2, D_all, I_all,
-                                                              id_offsets_dev, D_out, I_out);
+                                                              id_offsets, D_out, I_out);
     count_launch();
     return cudaGetLastError();
 }

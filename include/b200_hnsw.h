@@ -120,7 +120,8 @@ int64_t bh_launch_count(void);
  *    as used by IndexShards(successive_ids=true)) ------------------------------------
  * D_all / I_all: device, [nshard][nq][k], each list sorted best-first, I local to its
  * shard (-1 = empty). Writes device D_out/I_out [nq][k] with I + id_offsets[shard].
- * stream: cudaStream_t as void* (NULL = default stream). */
+ * stream: cudaStream_t as void* (NULL = default stream). Enqueued only: no allocation, no
+ * synchronisation (id_offsets is consumed before the call returns). nshard <= 64. */
 int bh_merge_topk_device(int nshard, int64_t nq, int64_t k, int metric, const float* D_all,
                          const int64_t* I_all, const int64_t* id_offsets /*host, [nshard]*/,
                          float* D_out, int64_t* I_out, void* stream);

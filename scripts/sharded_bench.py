@@ -14,14 +14,15 @@ from hnsw_b200.sharded import ShardedIndexHNSWFlat
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--n_shard", type=int, default=12_500_000)
-ap.add_argument("--d", type=int, default=96)
-ap.add_argument("--d1", type=int, default=12)
+ap.add_argument("--dim", dest="d", type=int, default=96)
+ap.add_argument("--latent", dest="d1", type=int, default=12)
 ap.add_argument("--M", type=int, default=32)
 ap.add_argument("--efc", type=int, default=200)
 ap.add_argument("--nq", type=int, default=10000)
 ap.add_argument("--k", type=int, default=10)
 ap.add_argument("--efs", type=str, default="32,64,128")
 ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--ip", type=int, default=0)
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -32,14 +33,18 @@ g = torch.Generator(device=dev); g.manual_seed(1338)            # shared project
 proj = torch.rand(a.d1, a.d, generator=g, device=dev)
 scale = torch.rand(a.d, generator=g, device=dev) * 4 + 0.1
 xq = torch.sin((torch.randn(a.nq, a.d1, generator=g, device=dev) @ proj) * scale).contiguous()
+if a.ip:
+    xq = (xq / xq.norm(dim=1, keepdim=True)).contiguous()
 g2 = torch.Generator(device=dev); g2.manual_seed(7000 + rank)    # this rank's shard
 xb = torch.empty(a.n_shard, a.d, device=dev)
 for i0 in range(0, a.n_shard, 1 << 20):
     i1 = min(a.n_shard, i0 + (1 << 20))
     xb[i0:i1] = torch.sin((torch.randn(i1 - i0, a.d1, generator=g2, device=dev) @ proj) * scale)
+    if a.ip:
+        xb[i0:i1] /= xb[i0:i1].norm(dim=1, keepdim=True)
 xb_h = xb.cpu().numpy()
 
-sh = ShardedIndexHNSWFlat(a.d, a.M, 1, device=dev)
+sh = ShardedIndexHNSWFlat(a.d, a.M, 0 if a.ip else 1, device=dev)
 sh.local.hnsw.efConstruction = a.efc
 torch.cuda.synchronize(); dist.barrier()
 t0 = time.time()
@@ -49,11 +54,11 @@ t_build = time.time() - t0
 del xb_h
 
 # global ground truth: per-shard exact top-k -> all-gather -> merge
-Dl, Il = exact_knn_torch(xb, xq, a.k, chunk=1 << 17)
+Dl, Il = exact_knn_torch(xb, xq, a.k, inner_product=bool(a.ip), chunk=1 << 17)
 Il = Il + int(sh.offsets[rank])
 Dall = torch.empty(world, a.nq, a.k, device=dev); Iall = torch.empty(world, a.nq, a.k, dtype=torch.int64, device=dev)
 dist.all_gather_into_tensor(Dall, Dl.contiguous()); dist.all_gather_into_tensor(Iall, Il.contiguous())
-sel = torch.topk(Dall.permute(1, 0, 2).reshape(a.nq, -1), a.k, dim=1, largest=False).indices
+sel = torch.topk(Dall.permute(1, 0, 2).reshape(a.nq, -1), a.k, dim=1, largest=bool(a.ip)).indices
 gt = torch.gather(Iall.permute(1, 0, 2).reshape(a.nq, -1), 1, sel).cpu().numpy()
 del xb, Dall, Iall
 torch.cuda.empty_cache()
@@ -75,7 +80,7 @@ for ef in [int(e) for e in a.efs.split(",")]:
     rows.append({"efSearch": ef, "ms_per_batch": round(float(ms.item()), 3), "qps": round(a.nq / float(ms.item()) * 1e3),
                  "recall_at_10": round(rec, 4)})
 if rank == 0:
-    print(json.dumps({"config": f"sharded {world} x {a.n_shard} x {a.d} fp32 L2, M={a.M} efC={a.efc}, {a.nq} queries broadcast, "
+    print(json.dumps({"config": f"sharded {world} x {a.n_shard} x {a.d} fp32 {'IP' if a.ip else 'L2'}, M={a.M} efC={a.efc}, {a.nq} queries broadcast, "
                                 f"all-gather {a.nq * a.k * 12} B/rank + merge kernel",
                       "db_vectors": world * a.n_shard, "n_gpus": world,
                       "build_s": round(t_build, 2), "build_vectors_per_s_total": round(world * a.n_shard / t_build),
