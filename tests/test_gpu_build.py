@@ -101,3 +101,43 @@ def test_add_with_preset_levels_and_order(oracle_mod):
     assert np.array_equal(idx.export_graph()["neighbors"], o.export_graph()["neighbors"])
     with pytest.raises(RuntimeError):
         idx.add(xb[:3], order=np.array([0, 1, 2], np.int32))      # not the new ids
+
+
+def test_add_on_top_of_imported_graph(oracle_mod):
+    """Imported rows have no verified prefix (nver = 0), so their first shrinks take the full
+    heuristic path; the result must still equal the oracle continuing the same build."""
+    import hnsw_b200
+    d, M = 32, 8
+    xb, xq = synthetic_dataset(d, 2200, 40)
+    o = oracle_mod.OracleHNSWFlat(d, M)
+    o.set_team(8)
+    o.add(xb[:1200])
+    g0 = o.export_graph()
+    idx = hnsw_b200.IndexHNSWFlat(d, M)
+    idx.import_graph(xb[:1200], g0["levels"], g0["neighbors"], g0["entry_point"], g0["max_level"])
+    lv = o.peek_levels(1000)
+    order = o.add(xb[1200:], return_order=True)
+    idx.set_build_params(max_batch=1)
+    idx.add(xb[1200:], levels=lv, order=order)
+    go, gg = o.export_graph(), idx.export_graph()
+    assert np.array_equal(gg["levels"], go["levels"])
+    mism = np.flatnonzero(gg["neighbors"] != go["neighbors"])
+    assert mism.size == 0, f"{mism.size} adjacency slots differ"
+    Do, Io = o.search(xq, 10, 40)
+    D, I = idx.search(xq, 10, efSearch=40)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do)
+
+
+@pytest.mark.parametrize("d,M,team,n", [(64, 64, 8, 900), (2048, 4, 32, 250)])
+def test_sequential_build_wide_rows_and_wide_vectors(oracle_mod, d, M, team, n):
+    xb, xq = synthetic_dataset(d, n, 20)
+    o = oracle_mod.OracleHNSWFlat(d, M)
+    o.set_team(team)
+    o.efConstruction = 48
+    o.add(xb)
+    idx = _build_gpu(xb, M, 48, 1, max_batch=1)
+    go, gg = o.export_graph(), idx.export_graph()
+    assert np.array_equal(gg["neighbors"], go["neighbors"])
+    Do, Io = o.search(xq, 10, 64)
+    D, I = idx.search(xq, 10, efSearch=64)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do)
