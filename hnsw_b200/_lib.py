@@ -45,6 +45,8 @@ _SIGS = {
     "bh_index_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int]),
     "bh_index_free": (C.c_int, [_P]),
     "bh_index_reset": (C.c_int, [_P]),
+    "bh_index_set_vector_storage": (C.c_int, [_P, C.c_int]),
+    "bh_index_get_vector_storage": (C.c_int, [_P]),
     "bh_index_train": (C.c_int, [_P, C.c_int64, _P]),
     "bh_index_add": (C.c_int, [_P, C.c_int64, _P]),
     "bh_index_add_ex": (C.c_int, [_P, C.c_int64, _P, _P, _P]),

@@ -80,17 +80,18 @@ __device__ inline GroupSmem carve_group_smem(unsigned char* p, int d, int ef, in
     return s;
 }
 
-template <int TEAM, int CPL, int W, int R>
+template <int TEAM, int CPL, int W, int R, bool HALF = false>
 struct Beam {
     static constexpr int TPW = 32 / TEAM;  // teams per warp
     static constexpr int NT = TPW * W;     // teams per query group
+    static constexpr int ES = HALF ? 2 : 1;  // float4s of query per 16-byte stored chunk
 
     const GraphView& g;
     const GroupSmem& s;
     const int wig;   // warp index within the group (0 = leader)
     const int lane;
     const int bar_id;
-    float4 q[CPL];   // this lane's slice of the query
+    float4 q[CPL][ES];  // this lane's slice of the query (fp32), laid out like the stored chunks
 
     __device__ Beam(const GraphView& g_, const GroupSmem& s_, int wig_, int lane_, int bar_id_)
         : g(g_), s(s_), wig(wig_), lane(lane_), bar_id(bar_id_) {}
@@ -102,12 +103,24 @@ struct Beam {
             bar_sync(bar_id, 32 * W);
     }
 
-    __device__ __forceinline__ void load_query_from_smem() {
+    // qbuf holds either an fp32 query (search) or a stored row (construction: fp32 or fp16).
+    __device__ __forceinline__ void load_query_from_smem(bool stored_row) {
         const int lit = lane % TEAM;
 #pragma unroll
         for (int c = 0; c < CPL; c++) {
             const int chunk = c * TEAM + lit;
-            q[c] = chunk < g.nchunk ? s.qbuf[chunk] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool ok = chunk < g.nchunk;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (!HALF) {
+                q[c][0] = ok ? s.qbuf[chunk] : z;
+            } else {
+                if (stored_row) {
+                    chunk_to_f32<true>(ok ? s.qbuf[chunk] : z, q[c]);
+                } else {
+                    q[c][0] = ok ? s.qbuf[2 * chunk] : z;
+                    q[c][1] = ok ? s.qbuf[2 * chunk + 1] : z;
+                }
+            }
         }
     }
 
@@ -163,23 +176,12 @@ struct Beam {
 #pragma unroll
             for (int k = 0; k < R; k++) {
                 float acc = 0.f;
-                if (l2) {
 #pragma unroll
-                    for (int c = 0; c < CPL; c++) {
-                        float t;
-                        t = q[c].x - x[k][c].x; acc = fmaf(t, t, acc);
-                        t = q[c].y - x[k][c].y; acc = fmaf(t, t, acc);
-                        t = q[c].z - x[k][c].z; acc = fmaf(t, t, acc);
-                        t = q[c].w - x[k][c].w; acc = fmaf(t, t, acc);
-                    }
-                } else {
+                for (int c = 0; c < CPL; c++) {
+                    float4 xf[ES];
+                    chunk_to_f32<HALF>(x[k][c], xf);
 #pragma unroll
-                    for (int c = 0; c < CPL; c++) {
-                        acc = fmaf(q[c].x, x[k][c].x, acc);
-                        acc = fmaf(q[c].y, x[k][c].y, acc);
-                        acc = fmaf(q[c].z, x[k][c].z, acc);
-                        acc = fmaf(q[c].w, x[k][c].w, acc);
-                    }
+                    for (int e = 0; e < ES; e++) acc4(acc, q[c][e], xf[e], l2);
                 }
 #pragma unroll
                 for (int off = TEAM / 2; off >= 1; off >>= 1)

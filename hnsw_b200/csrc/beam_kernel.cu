@@ -14,7 +14,7 @@
 
 namespace bh {
 
-template <int TEAM, int CPL, int W, int R, int G, int MINB>
+template <int TEAM, int CPL, int W, int R, int G, int MINB, bool HALF>
 __global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, BeamTask t) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, Bea
     const int rk = t.sel ? t.k : 0;
     const size_t gbytes = group_smem_bytes(g.d, t.ef, hash_slots, g.deg0, rk);
     const GroupSmem s = carve_group_smem(smem_raw + grp * gbytes, g.d, t.ef, hash_slots, g.deg0, rk);
-    Beam<TEAM, CPL, W, R> beam(g, s, wig, lane, 1 + grp);
+    Beam<TEAM, CPL, W, R, HALF> beam(g, s, wig, lane, 1 + grp);
 
     if (wig == 0 && lane == 0) {
         mbar_init(s.mbar, 1);
@@ -33,7 +33,8 @@ __global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, Bea
     }
     beam.group_sync();
     uint32_t phase = 0;
-    const uint32_t qbytes = (uint32_t)g.d * 4u;
+    const uint32_t qbytes_query = (uint32_t)g.d * 4u;             // fp32 query from the caller
+    const uint32_t qbytes_row = (uint32_t)g.nchunk * 16u;         // a stored row (fp32 or fp16)
 
     for (;;) {
         if (wig == 0 && lane == 0) s.ctrl[3] = atomicAdd(t.counter, 1);
@@ -42,10 +43,12 @@ __global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, Bea
         if (wi >= t.n_items) break;
 
         int level = 0, stop_level = 0;
-        const float* qsrc;
+        const void* qsrc;
+        uint32_t qbytes = qbytes_query;
         if (t.items) {  // construction: the query is the stored vector of the new point
             const int4 it = __ldg(t.items + wi);
-            qsrc = g.vecs + (size_t)it.x * g.d;
+            qsrc = reinterpret_cast<const char*>(g.vecs) + (size_t)it.x * qbytes_row;
+            qbytes = qbytes_row;
             level = it.y;
             stop_level = it.z;
         } else {
@@ -59,7 +62,7 @@ __global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, Bea
         }
         mbar_wait(s.mbar, phase);
         phase ^= 1;
-        beam.load_query_from_smem();
+        beam.load_query_from_smem(t.items != nullptr);
 
         BeamStats st;
         uint32_t cur_id = 0;
@@ -106,10 +109,10 @@ __global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, Bea
 // ---------------------------------------------------------------- host dispatch
 namespace {
 
-template <int TEAM, int CPL, int W, int R, int G, int MINB>
+template <int TEAM, int CPL, int W, int R, int G, int MINB, bool HALF>
 cudaError_t launch_one(const GraphView& g, const BeamTask& t, int num_sms, cudaStream_t stream,
                        int* grid_out) {
-    auto kern = beam_kernel<TEAM, CPL, W, R, G, MINB>;
+    auto kern = beam_kernel<TEAM, CPL, W, R, G, MINB, HALF>;
     const size_t smem = (size_t)G * group_smem_bytes(g.d, t.ef, 1 << t.hash_bits, g.deg0, t.sel ? t.k : 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -129,21 +132,35 @@ cudaError_t launch_one(const GraphView& g, const BeamTask& t, int num_sms, cudaS
 // variant (W == 1 only): 0 = R rows in flight per team, 4 blocks/SM (<=128 regs);
 // 1 = R/2 rows, 6 blocks/SM (<=80 regs); 2 = R/2 rows, 8 blocks/SM (<=64 regs);
 // 3 = R/2 rows, 5 blocks/SM (<=96 regs).
-template <int TEAM, int CPL, int R>
+template <int TEAM, int CPL, int R, bool HALF>
 cudaError_t launch_w(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
                      cudaStream_t stream, int* grid_out) {
     constexpr int RH = R >= 2 ? R / 2 : 1;
     switch (W) {
         case 1:
-            if (variant == 1) return launch_one<TEAM, CPL, 1, RH, 4, 6>(g, t, num_sms, stream, grid_out);
-            if (variant == 2) return launch_one<TEAM, CPL, 1, RH, 4, 8>(g, t, num_sms, stream, grid_out);
-            if (variant == 3) return launch_one<TEAM, CPL, 1, RH, 4, 5>(g, t, num_sms, stream, grid_out);
-            return launch_one<TEAM, CPL, 1, R, 4, 4>(g, t, num_sms, stream, grid_out);
-        case 2: return launch_one<TEAM, CPL, 2, R, 2, 1>(g, t, num_sms, stream, grid_out);
-        case 4: return launch_one<TEAM, CPL, 4, R, 1, 1>(g, t, num_sms, stream, grid_out);
-        case 8: return launch_one<TEAM, CPL, 8, R, 1, 1>(g, t, num_sms, stream, grid_out);
+            if (variant == 1) return launch_one<TEAM, CPL, 1, RH, 4, 6, HALF>(g, t, num_sms, stream, grid_out);
+            if (variant == 2) return launch_one<TEAM, CPL, 1, RH, 4, 8, HALF>(g, t, num_sms, stream, grid_out);
+            if (variant == 3) return launch_one<TEAM, CPL, 1, RH, 4, 5, HALF>(g, t, num_sms, stream, grid_out);
+            return launch_one<TEAM, CPL, 1, R, 4, 4, HALF>(g, t, num_sms, stream, grid_out);
+        case 2: return launch_one<TEAM, CPL, 2, R, 2, 1, HALF>(g, t, num_sms, stream, grid_out);
+        case 4: return launch_one<TEAM, CPL, 4, R, 1, 1, HALF>(g, t, num_sms, stream, grid_out);
+        case 8: return launch_one<TEAM, CPL, 8, R, 1, 1, HALF>(g, t, num_sms, stream, grid_out);
         default: return cudaErrorInvalidValue;
     }
+}
+
+// (TEAM, CPL) by the number of 16-byte chunks per stored row (fp32: d/4, fp16: d/8).
+template <bool HALF>
+cudaError_t launch_by_chunks(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
+                             cudaStream_t stream, int* grid_out) {
+    const int nc = g.nchunk;
+    if (nc <= 16) return launch_w<8, 2, 8, HALF>(g, t, W, variant, num_sms, stream, grid_out);  // 2 chunks/lane: 8 rows in flight
+    if (nc <= 32) return launch_w<8, 4, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out);
+    if (nc <= 64) return launch_w<16, 4, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out);
+    if (nc <= 128) return launch_w<32, 4, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out);
+    if (nc <= 256) return launch_w<32, 8, 2, HALF>(g, t, W, variant, num_sms, stream, grid_out);
+    if (nc <= 512) return launch_w<32, 16, 1, HALF>(g, t, W, variant, num_sms, stream, grid_out);
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace
@@ -154,13 +171,8 @@ size_t beam_group_smem(int d, int ef, int hash_bits, int deg, int rk) {
 
 cudaError_t launch_beam(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
                         cudaStream_t stream, int* grid_out) {
-    const int d = g.d;
-    if (d <= 128) return launch_w<8, 4, 4>(g, t, W, variant, num_sms, stream, grid_out);
-    if (d <= 256) return launch_w<16, 4, 4>(g, t, W, variant, num_sms, stream, grid_out);
-    if (d <= 512) return launch_w<32, 4, 4>(g, t, W, variant, num_sms, stream, grid_out);
-    if (d <= 1024) return launch_w<32, 8, 2>(g, t, W, variant, num_sms, stream, grid_out);
-    if (d <= 2048) return launch_w<32, 16, 1>(g, t, W, variant, num_sms, stream, grid_out);
-    return cudaErrorInvalidValue;
+    return g.half ? launch_by_chunks<true>(g, t, W, variant, num_sms, stream, grid_out)
+                  : launch_by_chunks<false>(g, t, W, variant, num_sms, stream, grid_out);
 }
 
 }  // namespace bh

@@ -18,16 +18,30 @@ namespace {
 
 constexpr int kChainCap = 64;
 
-template <int TEAM, int CPL>
+// One stored vector, sliced over the TEAM lanes of a team: lane `lit` owns the 16-byte chunks
+// lit, lit+TEAM, ... `raw` keeps them as stored (fp32 x4 or fp16 x8; used to stage vectors in
+// shared memory), `f` is their exact fp32 widening used for arithmetic.
+template <int TEAM, int CPL, bool HALF>
 struct TeamVec {
-    float4 x[CPL];
+    static constexpr int ES = HALF ? 2 : 1;
+    float4 raw[CPL];
+    float4 f[CPL][ES];
+    __device__ __forceinline__ void set_raw(int c, const float4& v) {
+        raw[c] = v;
+        chunk_to_f32<HALF>(v, f[c]);
+    }
     // Load this lane's slice of a stored vector (generic pointer: global or shared).
     __device__ __forceinline__ void load(const float4* row, int nchunk, int lit, bool valid) {
 #pragma unroll
         for (int c = 0; c < CPL; c++) {
             const int chunk = c * TEAM + lit;
-            x[c] = (valid && chunk < nchunk) ? row[chunk] : make_float4(0.f, 0.f, 0.f, 0.f);
+            set_raw(c, (valid && chunk < nchunk) ? row[chunk] : make_float4(0.f, 0.f, 0.f, 0.f));
         }
+    }
+    __device__ __forceinline__ float reduce(float acc, bool is_l2) const {
+#pragma unroll
+        for (int off = TEAM / 2; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
+        return is_l2 ? acc : -acc;
     }
     // Same arithmetic as Beam::compute_dists: one fmaf chain per lane, xor-butterfly over the team.
     __device__ __forceinline__ float dist(const float4* row, int nchunk, int lit, bool is_l2) const {
@@ -36,44 +50,21 @@ struct TeamVec {
         for (int c = 0; c < CPL; c++) {
             const int chunk = c * TEAM + lit;
             const float4 u = chunk < nchunk ? row[chunk] : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (is_l2) {
-                float t;
-                t = u.x - x[c].x; acc = fmaf(t, t, acc);
-                t = u.y - x[c].y; acc = fmaf(t, t, acc);
-                t = u.z - x[c].z; acc = fmaf(t, t, acc);
-                t = u.w - x[c].w; acc = fmaf(t, t, acc);
-            } else {
-                acc = fmaf(u.x, x[c].x, acc);
-                acc = fmaf(u.y, x[c].y, acc);
-                acc = fmaf(u.z, x[c].z, acc);
-                acc = fmaf(u.w, x[c].w, acc);
-            }
-        }
+            float4 uf[ES];
+            chunk_to_f32<HALF>(u, uf);
 #pragma unroll
-        for (int off = TEAM / 2; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
-        return is_l2 ? acc : -acc;
+            for (int e = 0; e < ES; e++) acc4(acc, uf[e], f[c][e], is_l2);
+        }
+        return reduce(acc, is_l2);
     }
-    // Distance to a vector held in another lane-sliced register array (same arithmetic).
-    __device__ __forceinline__ float dist(const float4 (&o)[CPL], int nchunk, int lit, bool is_l2, bool) const {
+    // Distance to a vector held in another TeamVec (same arithmetic).
+    __device__ __forceinline__ float dist(const TeamVec& o, bool is_l2) const {
         float acc = 0.f;
 #pragma unroll
-        for (int c = 0; c < CPL; c++) {
-            if (is_l2) {
-                float t;
-                t = o[c].x - x[c].x; acc = fmaf(t, t, acc);
-                t = o[c].y - x[c].y; acc = fmaf(t, t, acc);
-                t = o[c].z - x[c].z; acc = fmaf(t, t, acc);
-                t = o[c].w - x[c].w; acc = fmaf(t, t, acc);
-            } else {
-                acc = fmaf(o[c].x, x[c].x, acc);
-                acc = fmaf(o[c].y, x[c].y, acc);
-                acc = fmaf(o[c].z, x[c].z, acc);
-                acc = fmaf(o[c].w, x[c].w, acc);
-            }
-        }
+        for (int c = 0; c < CPL; c++)
 #pragma unroll
-        for (int off = TEAM / 2; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
-        return is_l2 ? acc : -acc;
+            for (int e = 0; e < ES; e++) acc4(acc, o.f[c][e], f[c][e], is_l2);
+        return reduce(acc, is_l2);
     }
     // Four independent pairs at once (same per-pair arithmetic; the four fmaf chains interleave).
     __device__ __forceinline__ void dist4(const float4* r0, const float4* r1, const float4* r2,
@@ -90,18 +81,10 @@ struct TeamVec {
                 u[p] = chunk < nchunk ? rows[p][chunk] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int p = 0; p < 4; p++) {
-                if (is_l2) {
-                    float t;
-                    t = u[p].x - x[c].x; acc[p] = fmaf(t, t, acc[p]);
-                    t = u[p].y - x[c].y; acc[p] = fmaf(t, t, acc[p]);
-                    t = u[p].z - x[c].z; acc[p] = fmaf(t, t, acc[p]);
-                    t = u[p].w - x[c].w; acc[p] = fmaf(t, t, acc[p]);
-                } else {
-                    acc[p] = fmaf(u[p].x, x[c].x, acc[p]);
-                    acc[p] = fmaf(u[p].y, x[c].y, acc[p]);
-                    acc[p] = fmaf(u[p].z, x[c].z, acc[p]);
-                    acc[p] = fmaf(u[p].w, x[c].w, acc[p]);
-                }
+                float4 uf[ES];
+                chunk_to_f32<HALF>(u[p], uf);
+#pragma unroll
+                for (int e = 0; e < ES; e++) acc4(acc[p], uf[e], f[c][e], is_l2);
             }
         }
 #pragma unroll
@@ -124,7 +107,7 @@ struct TeamVec {
 //                   cand_slot[c]; kept vectors are read back from their slots (kept_slot[]).
 // 32/TEAM candidates are examined per step, one per team; dependencies inside a step are
 // resolved in candidate order, so the outcome equals the sequential scan.
-template <int TEAM, int CPL, bool STAGED>
+template <int TEAM, int CPL, bool STAGED, bool HALF>
 __device__ int heuristic(const GraphView& g, const unsigned long long* cand, int n, int max_size,
                          unsigned long long* kept_key, float4* kvec, const float4* stage,
                          const int32_t* cand_slot, int32_t* kept_slot, int lane) {
@@ -133,7 +116,7 @@ __device__ int heuristic(const GraphView& g, const unsigned long long* cand, int
     const float4* __restrict__ vecs = reinterpret_cast<const float4*>(g.vecs);
     const bool is_l2 = g.is_l2 != 0;
     int K = 0;
-    TeamVec<TEAM, CPL> nxt;
+    TeamVec<TEAM, CPL, HALF> nxt;
     unsigned long long nxt_key = ~0ull;
     int nxt_slot = 0;
     auto fetch = [&](int c0) {
@@ -149,7 +132,7 @@ __device__ int heuristic(const GraphView& g, const unsigned long long* cand, int
     };
     fetch(0);
     for (int c0 = 0; c0 < n && K < max_size; c0 += TPW) {
-        const TeamVec<TEAM, CPL> v = nxt;
+        const TeamVec<TEAM, CPL, HALF> v = nxt;
         const unsigned long long key = nxt_key;
         const int slot = nxt_slot;
         const bool valid = c0 + team < n;
@@ -186,7 +169,7 @@ __device__ int heuristic(const GraphView& g, const unsigned long long* cand, int
 #pragma unroll
                     for (int cc = 0; cc < CPL; cc++) {
                         const int chunk = cc * TEAM + lit;
-                        if (chunk < g.nchunk) kvec[(size_t)K * g.nchunk + chunk] = v.x[cc];
+                        if (chunk < g.nchunk) kvec[(size_t)K * g.nchunk + chunk] = v.raw[cc];
                     }
                 }
             }
@@ -278,11 +261,11 @@ __device__ inline WarpSmem carve_warp_smem(unsigned char* p, int d, int deg0, bo
 }
 
 // ---- forward links + back-edge staging: one warp per (point, level) item ------------
-template <int TEAM, int CPL>
+template <int TEAM, int CPL, bool HALF>
 __global__ void __launch_bounds__(64) select_and_link_kernel(GraphView g, BuildBatch b, int use_kvec) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const WarpSmem w = carve_warp_smem(smem_raw + wib * warp_smem_bytes(g.d, g.deg0, use_kvec), g.d,
+    const WarpSmem w = carve_warp_smem(smem_raw + wib * warp_smem_bytes(g.nchunk * 4, g.deg0, use_kvec), g.nchunk * 4,
                                        g.deg0, use_kvec);
     const int nwarps = gridDim.x * (blockDim.x >> 5);
     for (int item = blockIdx.x * (blockDim.x >> 5) + wib; item < b.n_items; item += nwarps) {
@@ -300,7 +283,7 @@ __global__ void __launch_bounds__(64) select_and_link_kernel(GraphView g, BuildB
             kept = cand;
         } else {
             verified = true;
-            K = heuristic<TEAM, CPL, false>(g, cand, n, deg, w.kept_key, w.vbuf, nullptr, nullptr, nullptr, lane);
+            K = heuristic<TEAM, CPL, false, HALF>(g, cand, n, deg, w.kept_key, w.vbuf, nullptr, nullptr, nullptr, lane);
             kept = w.kept_key;
         }
         __syncwarp();
@@ -339,15 +322,15 @@ __global__ void __launch_bounds__(64) select_and_link_kernel(GraphView g, BuildB
 // the 2M+1 vectors once, scoring each against the owner and against the (few) specials, and then
 // replays the heuristic on that small table — the same comparisons on the same values as the full
 // run, hence the identical result, at ~1/10 of the arithmetic and no large shared-memory stage.
-template <int TEAM, int CPL>
+template <int TEAM, int CPL, bool HALF>
 __global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b, int use_kvec) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int TPW = 32 / TEAM;
     constexpr int kGR = 4;  // candidate rows in flight per team
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int lit = lane % TEAM, team = lane / TEAM;
-    const WarpSmem w = carve_warp_smem(smem_raw + wib * warp_smem_bytes(g.d, g.deg0, false, b.max_special),
-                                       g.d, g.deg0, false, b.max_special);
+    const WarpSmem w = carve_warp_smem(smem_raw + wib * warp_smem_bytes(g.nchunk * 4, g.deg0, false, b.max_special),
+                                       g.nchunk * 4, g.deg0, false, b.max_special);
     const float4* __restrict__ vecs = reinterpret_cast<const float4*>(g.vecs);
     const bool is_l2 = g.is_l2 != 0;
     const int stride = g.deg0 + 8;
@@ -380,7 +363,7 @@ __global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b,
         uint8_t* nvp = nver_ptr(g, b, dst, level);
         int nv = *nvp;
         const int nv0 = nv;
-        TeamVec<TEAM, CPL> q;  // the destination vertex's own vector (base of the distances)
+        TeamVec<TEAM, CPL, HALF> q;  // the destination vertex's own vector (base of the distances)
         bool q_loaded = false;
 
         for (int done = 0; done < c; done++) {
@@ -441,12 +424,12 @@ __global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b,
                     const int si = s0 + team;
                     if (si < ns) {
                         const int id = si == 0 ? src : w.rowid[nv + si - 1];
-                        TeamVec<TEAM, CPL> tv;
+                        TeamVec<TEAM, CPL, HALF> tv;
                         tv.load(vecs + (size_t)id * g.nchunk, g.nchunk, lit, true);
 #pragma unroll
                         for (int c2 = 0; c2 < CPL; c2++) {
                             const int chunk = c2 * TEAM + lit;
-                            if (chunk < g.nchunk) w.spec_vec[(size_t)si * g.nchunk + chunk] = tv.x[c2];
+                            if (chunk < g.nchunk) w.spec_vec[(size_t)si * g.nchunk + chunk] = tv.raw[c2];
                         }
                     }
                 }
@@ -454,7 +437,7 @@ __global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b,
             }
             // stream every candidate once: distance to the owner (+ to each special)
             for (int r0 = 0; r0 < n; r0 += TPW * kGR) {
-                TeamVec<TEAM, CPL> x[kGR];
+                TeamVec<TEAM, CPL, HALF> x[kGR];
                 int cid[kGR];
 #pragma unroll
                 for (int k2 = 0; k2 < kGR; k2++) {
@@ -464,14 +447,14 @@ __global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b,
 #pragma unroll
                     for (int c2 = 0; c2 < CPL; c2++) {
                         const int chunk = c2 * TEAM + lit;
-                        x[k2].x[c2] = (cid[k2] >= 0 && chunk < g.nchunk) ? ldg_stream(rowv + chunk)
-                                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                        x[k2].set_raw(c2, (cid[k2] >= 0 && chunk < g.nchunk) ? ldg_stream(rowv + chunk)
+                                                                            : make_float4(0.f, 0.f, 0.f, 0.f));
                     }
                 }
 #pragma unroll
                 for (int k2 = 0; k2 < kGR; k2++) {
                     const int a = r0 + k2 * TPW + team;
-                    const float dd = x[k2].dist(q.x, g.nchunk, lit, is_l2, true);
+                    const float dd = x[k2].dist(q, is_l2);
                     if (cid[k2] >= 0 && lit == 0)
                         w.cand_a[a] = a == 0 ? pack_key(d_src, (uint32_t)src) : pack_key(dd, (uint32_t)cid[k2]);
                     if (incremental) {
@@ -521,7 +504,7 @@ __global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b,
                     if (K >= deg) break;
                 }
             } else {
-                K = heuristic<TEAM, CPL, false>(g, w.cand_b, n, deg, w.kept_key, nullptr, nullptr, nullptr,
+                K = heuristic<TEAM, CPL, false, HALF>(g, w.cand_b, n, deg, w.kept_key, nullptr, nullptr, nullptr,
                                                 nullptr, lane);
             }
             __syncwarp();
@@ -533,15 +516,15 @@ __global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b,
     }
 }
 
-template <int TEAM, int CPL>
+template <int TEAM, int CPL, bool HALF>
 cudaError_t launch_build_pair(bool backlinks, const GraphView& g, const BuildBatch& b, int num_sms,
                               cudaStream_t stream) {
     const int wpb = 2;
     cudaError_t e;
     if (!backlinks) {
-        const bool kvec = (size_t)(g.deg0 + 1) * g.d * 4 <= 48 * 1024;
-        const size_t smem = wpb * warp_smem_bytes(g.d, g.deg0, kvec);
-        auto ks = select_and_link_kernel<TEAM, CPL>;
+        const bool kvec = (size_t)(g.deg0 + 1) * g.nchunk * 16 <= 48 * 1024;
+        const size_t smem = wpb * warp_smem_bytes(g.nchunk * 4, g.deg0, kvec);
+        auto ks = select_and_link_kernel<TEAM, CPL, HALF>;
         e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int occ = 1;
@@ -552,8 +535,8 @@ cudaError_t launch_build_pair(bool backlinks, const GraphView& g, const BuildBat
         if (grid < 1) grid = 1;
         ks<<<(unsigned)grid, 32 * wpb, smem, stream>>>(g, b, (int)kvec);
     } else {
-        const size_t smem = wpb * warp_smem_bytes(g.d, g.deg0, false, b.max_special);
-        auto kb = backlink_kernel<TEAM, CPL>;
+        const size_t smem = wpb * warp_smem_bytes(g.nchunk * 4, g.deg0, false, b.max_special);
+        auto kb = backlink_kernel<TEAM, CPL, HALF>;
         e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int occ = 1;
@@ -567,15 +550,23 @@ cudaError_t launch_build_pair(bool backlinks, const GraphView& g, const BuildBat
     return cudaGetLastError();
 }
 
+template <bool HALF>
+cudaError_t dispatch_build_t(bool backlinks, const GraphView& g, const BuildBatch& b, int num_sms,
+                             cudaStream_t stream) {
+    const int nc = g.nchunk;  // same (TEAM, CPL) table as the traversal kernel
+    if (nc <= 16) return launch_build_pair<8, 2, HALF>(backlinks, g, b, num_sms, stream);
+    if (nc <= 32) return launch_build_pair<8, 4, HALF>(backlinks, g, b, num_sms, stream);
+    if (nc <= 64) return launch_build_pair<16, 4, HALF>(backlinks, g, b, num_sms, stream);
+    if (nc <= 128) return launch_build_pair<32, 4, HALF>(backlinks, g, b, num_sms, stream);
+    if (nc <= 256) return launch_build_pair<32, 8, HALF>(backlinks, g, b, num_sms, stream);
+    if (nc <= 512) return launch_build_pair<32, 16, HALF>(backlinks, g, b, num_sms, stream);
+    return cudaErrorInvalidValue;
+}
+
 cudaError_t dispatch_build(bool backlinks, const GraphView& g, const BuildBatch& b, int num_sms,
                            cudaStream_t stream) {
-    const int d = g.d;
-    if (d <= 128) return launch_build_pair<8, 4>(backlinks, g, b, num_sms, stream);
-    if (d <= 256) return launch_build_pair<16, 4>(backlinks, g, b, num_sms, stream);
-    if (d <= 512) return launch_build_pair<32, 4>(backlinks, g, b, num_sms, stream);
-    if (d <= 1024) return launch_build_pair<32, 8>(backlinks, g, b, num_sms, stream);
-    if (d <= 2048) return launch_build_pair<32, 16>(backlinks, g, b, num_sms, stream);
-    return cudaErrorInvalidValue;
+    return g.half ? dispatch_build_t<true>(backlinks, g, b, num_sms, stream)
+                  : dispatch_build_t<false>(backlinks, g, b, num_sms, stream);
 }
 
 }  // namespace

@@ -79,6 +79,7 @@ int ceil_log2(long long v) {
 
 struct bh_index {
     int d = 0, M = 0, metric = BH_METRIC_L2, device = 0;
+    int storage = BH_STORAGE_F32;  // BH_STORAGE_F16: rows held as fp16 (opt-in)
     int efSearch = 16, efConstruction = 40;  // faiss HNSW defaults (App. A.1)
     bool check_relative_distance = true;
     bh_build_params bp{0, 0, 0, 0};
@@ -116,6 +117,9 @@ struct bh_index {
     DevBuf<float> e_dist;
 
     int deg0() const { return 2 * M; }
+    bool half() const { return storage == BH_STORAGE_F16; }
+    int row_floats() const { return half() ? d / 2 : d; }  // stored row size in 4-byte units
+    mutable DevBuf<float> conv_d;                           // fp32 staging for fp16 conversion
 
     bh::GraphView view() const {
         bh::GraphView g;
@@ -124,7 +128,8 @@ struct bh_index {
         g.upper_base = upper_base_d.p;
         g.upper_nbr = upper_nbr.p;
         g.d = d;
-        g.nchunk = d / 4;
+        g.nchunk = row_floats() / 4;
+        g.half = half() ? 1 : 0;
         g.deg0 = deg0();
         g.degU = M;
         g.entry_point = entry_point;
@@ -199,9 +204,10 @@ struct bh_index {
 
     int ensure_capacity(int64_t n_new_total, int64_t upper_rows_total) {
         const int64_t old_n = ntotal;
-        if ((size_t)n_new_total > (size_t)(vecs.cap / d)) {
-            int64_t cap = std::max<int64_t>(n_new_total, (int64_t)(vecs.cap / d) * 3 / 2);
-            BH_CUDA(vecs.reserve((size_t)cap * d, stream, true, (size_t)old_n * d));
+        const int rf = row_floats();
+        if ((size_t)n_new_total > (size_t)(vecs.cap / rf)) {
+            int64_t cap = std::max<int64_t>(n_new_total, (int64_t)(vecs.cap / rf) * 3 / 2);
+            BH_CUDA(vecs.reserve((size_t)cap * rf, stream, true, (size_t)old_n * rf));
             BH_CUDA(nbr0.reserve((size_t)cap * deg0(), stream, true, (size_t)old_n * deg0()));
             BH_CUDA(upper_base_d.reserve((size_t)cap, stream, true, (size_t)old_n));
             BH_CUDA(nver0.reserve((size_t)cap, stream, true, (size_t)old_n));
@@ -212,7 +218,7 @@ struct bh_index {
             BH_CUDA(nverU.reserve(cap / M + 1, stream, true, (size_t)n_upper_rows));
         }
         // pending-list heads: one per adjacency row, all -1 between batches
-        const int64_t level0_rows = (int64_t)(vecs.cap / d);
+        const int64_t level0_rows = (int64_t)(vecs.cap / row_floats());
         const size_t need = (size_t)level0_rows + upper_nbr.cap / M + 1;
         if (need > slot_head.cap || level0_rows != slot_level0) {
             BH_CUDA(slot_head.reserve(need, stream));
@@ -225,7 +231,7 @@ struct bh_index {
     void free_all() {
         nver0.release(); nverU.release();
         vecs.release(); nbr0.release(); upper_base_d.release(); upper_nbr.release(); slot_head.release();
-        sel_d.release();
+        sel_d.release(); conv_d.release();
         counter.release(); q_d.release(); D_d.release(); I_d.release(); stats_d.release();
         items_d.release(); cand_lists.release(); cand_counts.release();
         e_slot.release(); e_src.release(); e_dst.release(); e_level.release(); e_next.release(); e_dist.release();
@@ -233,6 +239,26 @@ struct bh_index {
 };
 
 namespace {
+
+// storage->add: rows [n0, n0+n) into HBM, converting to fp16 on the device when that storage is on
+int upload_vectors(bh_index* h, int64_t n0, int64_t n, const float* x) {
+    const int d = h->d;
+    if (!h->half()) {
+        BH_CUDA(cudaMemcpyAsync(h->vecs.p + (size_t)n0 * d, x, (size_t)n * d * sizeof(float),
+                                cudaMemcpyHostToDevice, h->stream));
+        return 0;
+    }
+    const int64_t chunk = std::min<int64_t>(n, 1 << 20);
+    BH_CUDA(h->conv_d.reserve((size_t)chunk * d, h->stream));
+    char* dst = reinterpret_cast<char*>(h->vecs.p);
+    for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+        const int64_t m = std::min(chunk, n - i0);
+        BH_CUDA(cudaMemcpyAsync(h->conv_d.p, x + (size_t)i0 * d, (size_t)m * d * sizeof(float),
+                                cudaMemcpyHostToDevice, h->stream));
+        BH_CUDA(bh::launch_f32_to_f16(h->conv_d.p, dst + (size_t)(n0 + i0) * d * 2, (size_t)m * d, h->stream));
+    }
+    return 0;
+}
 
 int search_device_impl(const bh_index* h, int64_t n, const float* xq_d, int64_t k, float* D_d,
                        int64_t* I_d, int32_t* stats_d, const bh_search_params* params,
@@ -348,8 +374,7 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     lap("ensure_capacity (cudaMalloc)");
 
     // -- storage->add: vectors into HBM; new rows = -1
-    BH_CUDA(cudaMemcpyAsync(h->vecs.p + (size_t)n0 * d, x, (size_t)n * d * sizeof(float),
-                            cudaMemcpyHostToDevice, h->stream));
+    if (int rc = upload_vectors(h, n0, n, x)) return rc;
     BH_CUDA(cudaMemsetAsync(h->nbr0.p + (size_t)n0 * deg0, 0xFF, (size_t)n * deg0 * sizeof(int32_t), h->stream));
     if (upper_rows > h->n_upper_rows)
         BH_CUDA(cudaMemsetAsync(h->upper_nbr.p + (size_t)h->n_upper_rows * M, 0xFF,
@@ -495,7 +520,7 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
             b.n_level0 = h->slot_level0;
             b.nver0 = h->nver0.p;
             b.nverU = h->nverU.p;
-            b.max_special = std::min(8, std::max(2, (16 * 1024) / (4 * d)));
+            b.max_special = std::min(8, std::max(2, (16 * 1024) / (4 * h->row_floats())));
             BH_CUDA(bh::launch_select_and_link(g, b, h->num_sms, h->stream));
             BH_CUDA(bh::launch_backlinks(g, b, h->num_sms, h->stream));
             bh::count_launch(3);
@@ -582,6 +607,26 @@ int bh_index_reset(bh_index* h) {
     // faiss IndexHNSW::reset → hnsw.reset() keeps the RNG state; so do we.
     return 0;
 }
+
+int bh_index_set_vector_storage(bh_index* h, int storage) {
+    if (!h) return fail("null index");
+    if (storage != BH_STORAGE_F32 && storage != BH_STORAGE_F16) return fail("unknown storage kind");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->ntotal != 0) return fail("set_vector_storage: the index is not empty");
+    if (storage == BH_STORAGE_F16 && h->d % 8 != 0) return fail("fp16 storage needs d % 8 == 0");
+    if (storage != h->storage) {  // capacities are counted in rows of the old width: start over
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream);
+        h->vecs.release();
+        h->nbr0.release();
+        h->upper_base_d.release();
+        h->nver0.release();
+        h->slot_level0 = 0;
+    }
+    h->storage = storage;
+    return 0;
+}
+int bh_index_get_vector_storage(const bh_index* h) { return h ? h->storage : -1; }
 
 int bh_index_train(bh_index* h, int64_t, const float*) {
     if (!h) return fail("null index");
@@ -701,20 +746,30 @@ int bh_index_search(const bh_index* h, int64_t n, const float* x, int64_t k, flo
 int bh_index_reconstruct(const bh_index* h, int64_t key, float* out) {
     if (!h) return fail("null index");
     if (key < 0 || key >= h->ntotal) return fail("reconstruct: key out of range");
-    BH_CUDA(cudaSetDevice(h->device));
-    BH_CUDA(cudaMemcpyAsync(out, h->vecs.p + (size_t)key * h->d, (size_t)h->d * sizeof(float),
-                            cudaMemcpyDeviceToHost, h->stream));
-    BH_CUDA(cudaStreamSynchronize(h->stream));
-    return 0;
+    return bh_index_reconstruct_n(h, key, 1, out);
 }
 
 int bh_index_reconstruct_n(const bh_index* h, int64_t i0, int64_t ni, float* out) {
     if (!h) return fail("null index");
     if (i0 < 0 || ni < 0 || i0 + ni > h->ntotal) return fail("reconstruct_n: range out of bounds");
     if (ni == 0) return 0;
+    std::lock_guard<std::mutex> lk(h->mu);
     BH_CUDA(cudaSetDevice(h->device));
-    BH_CUDA(cudaMemcpyAsync(out, h->vecs.p + (size_t)i0 * h->d, (size_t)ni * h->d * sizeof(float),
-                            cudaMemcpyDeviceToHost, h->stream));
+    if (!h->half()) {
+        BH_CUDA(cudaMemcpyAsync(out, h->vecs.p + (size_t)i0 * h->d, (size_t)ni * h->d * sizeof(float),
+                                cudaMemcpyDeviceToHost, h->stream));
+    } else {  // widen on the device (exact), then copy: the caller always sees fp32
+        const int64_t chunk = std::min<int64_t>(ni, 1 << 20);
+        BH_CUDA(h->conv_d.reserve((size_t)chunk * h->d, h->stream));
+        const char* src = reinterpret_cast<const char*>(h->vecs.p);
+        for (int64_t j0 = 0; j0 < ni; j0 += chunk) {
+            const int64_t m = std::min(chunk, ni - j0);
+            BH_CUDA(bh::launch_f16_to_f32(src + (size_t)(i0 + j0) * h->d * 2, h->conv_d.p, (size_t)m * h->d, h->stream));
+            BH_CUDA(cudaMemcpyAsync(out + (size_t)j0 * h->d, h->conv_d.p, (size_t)m * h->d * sizeof(float),
+                                    cudaMemcpyDeviceToHost, h->stream));
+            BH_CUDA(cudaStreamSynchronize(h->stream));
+        }
+    }
     BH_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -816,7 +871,7 @@ int bh_index_import_graph(bh_index* h, int64_t n, const float* x, const int32_t*
     for (size_t i = 0; i < up.size(); i++)
         if (up[i] < -1 || up[i] >= n) return fail("import: neighbor id out of range");
     if (int rc = h->ensure_capacity(n, upper_rows)) return rc;
-    BH_CUDA(cudaMemcpyAsync(h->vecs.p, x, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (int rc = upload_vectors(h, 0, n, x)) return rc;
     BH_CUDA(cudaMemcpyAsync(h->nbr0.p, l0.data(), l0.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     if (!up.empty())
         BH_CUDA(cudaMemcpyAsync(h->upper_nbr.p, up.data(), up.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));

@@ -1,5 +1,6 @@
 // common.cuh — shared device/host helpers for the sm_100a HNSW kernels.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -11,7 +12,9 @@ constexpr int kMaxDeg = 128;                       // 2*M <= 128
 constexpr int kMaxIdsPerLane = kMaxDeg / 32;
 
 // Device-side view of one index shard (SURVEY §8a1/a2 re-laid-out for HBM):
-//   vecs       fp32 [ntotal][d] row-major (faiss IndexFlat codes)
+//   vecs       [ntotal][d] row-major (faiss IndexFlat codes): fp32, or IEEE fp16 when `half` is set
+//              (opt-in storage mode). Either way a row is `nchunk` 16-byte chunks, so row addressing
+//              is the same; only a chunk's interpretation differs (4 floats vs 8 halfs).
 //   nbr0       int32 [ntotal][deg0]   level-0 rows, deg0 = 2M, -1 terminated
 //   upper_base int32 [ntotal]         first upper row of vertex i (in rows of degU), -1 if level 0
 //   upper_nbr  int32 [nupper][degU]   rows for levels 1..L of a vertex are consecutive
@@ -21,7 +24,8 @@ struct GraphView {
     const int32_t* upper_base;
     int32_t* upper_nbr;
     int d;
-    int nchunk;  // d / 4
+    int nchunk;  // 16-byte chunks per stored row: d / 4 (fp32) or d / 8 (fp16)
+    int half;    // 1 = fp16 storage
     int deg0;
     int degU;
     int entry_point;
@@ -51,6 +55,36 @@ __device__ __forceinline__ unsigned long long key_clean(unsigned long long k) { 
 
 __device__ __forceinline__ uint32_t hash_id(uint32_t id, int bits) {
     return (id * 2654435761u) >> (32 - bits);
+}
+
+// ---- stored chunk -> fp32 --------------------------------------------------------------
+// ES = float4s per 16-byte stored chunk (1: fp32 storage, 2: fp16 storage, exact widening).
+template <bool HALF>
+__device__ __forceinline__ void chunk_to_f32(const float4& raw, float4 (&out)[HALF ? 2 : 1]) {
+    if constexpr (!HALF) {
+        out[0] = raw;
+    } else {
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+        const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+        const float2 c = __half22float2(h[2]), d = __half22float2(h[3]);
+        out[0] = make_float4(a.x, a.y, b.x, b.y);
+        out[1] = make_float4(c.x, c.y, d.x, d.y);
+    }
+}
+// acc += sum over the 4 lanes of (a-b)^2 (L2) or a*b (IP), one fmaf chain, fixed order x,y,z,w.
+__device__ __forceinline__ void acc4(float& acc, const float4& a, const float4& b, bool l2) {
+    if (l2) {
+        float t;
+        t = a.x - b.x; acc = fmaf(t, t, acc);
+        t = a.y - b.y; acc = fmaf(t, t, acc);
+        t = a.z - b.z; acc = fmaf(t, t, acc);
+        t = a.w - b.w; acc = fmaf(t, t, acc);
+    } else {
+        acc = fmaf(a.x, b.x, acc);
+        acc = fmaf(a.y, b.y, acc);
+        acc = fmaf(a.z, b.z, acc);
+        acc = fmaf(a.w, b.w, acc);
+    }
 }
 
 // ---- mbarrier + 1-D bulk TMA (cp.async.bulk → UBLKCP in SASS) -------------------

@@ -69,6 +69,10 @@ cudaError_t launch_merge_topk(int nshard, int64_t nq, int k, int is_l2, const fl
                               const int64_t* I_all, const ShardOffsets& id_offsets, float* D_out,
                               int64_t* I_out, cudaStream_t stream);
 
+// ---- storage conversion (merge_kernel.cu): fp32 rows <-> fp16 rows, element-wise RNE / exact widening
+cudaError_t launch_f32_to_f16(const float* src, void* dst, size_t n, cudaStream_t stream);
+cudaError_t launch_f16_to_f32(const void* src, float* dst, size_t n, cudaStream_t stream);
+
 void count_launch(int n = 1);
 
 }  // namespace bh

@@ -5,6 +5,8 @@
 // lists, each sorted best-first. Each element's final rank is the number of elements, over all
 // shard lists, that precede it (binary search per list; ties broken by shard then position), so
 // the merge is a scatter with no serial heap.
+#include <algorithm>
+
 #include "engine.h"
 
 namespace bh {
@@ -49,7 +51,31 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(int nshard, int64_t nq,
     }
 }
 
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = __float2half_rn(src[i]);
+}
+__global__ void f16_to_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = __half2float(src[i]);
+}
+
 }  // namespace
+
+cudaError_t launch_f32_to_f16(const float* src, void* dst, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 32);
+    f32_to_f16_kernel<<<grid, 256, 0, stream>>>(src, static_cast<__half*>(dst), n);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_f16_to_f32(const void* src, float* dst, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 32);
+    f16_to_f32_kernel<<<grid, 256, 0, stream>>>(static_cast<const __half*>(src), dst, n);
+    count_launch();
+    return cudaGetLastError();
+}
 
 cudaError_t launch_merge_topk(int nshard, int64_t nq, int k, int is_l2, const float* D_all,
                               const int64_t* I_all, const ShardOffsets& id_offsets, float* D_out,

@@ -53,6 +53,11 @@ typedef struct bh_build_params {
     int32_t hash_bits;       /* 0: auto */
 } bh_build_params;
 
+/* vector storage inside the index (the API is fp32 either way) */
+#define BH_STORAGE_F32 0 /* faiss IndexFlat codes: the default, bit-comparable to faiss */
+#define BH_STORAGE_F16 1 /* opt-in: rows rounded to IEEE fp16 on add, fp32 accumulation; halves the gather
+                            bytes; distances differ from fp32 storage by ~1e-3 relative; needs d % 8 == 0 */
+
 /* -- lifecycle ------------------------------------------------------------------- */
 /* replaces faiss::IndexHNSWFlat::IndexHNSWFlat(int d, int M, MetricType metric) */
 int bh_index_create(bh_index** out, int d, int M, int metric, int device);
@@ -60,6 +65,10 @@ int bh_index_create(bh_index** out, int d, int M, int metric, int device);
 int bh_index_free(bh_index* h);
 /* replaces faiss::IndexHNSW::reset */
 int bh_index_reset(bh_index* h);
+/* extension (no faiss equivalent; closest: IndexHNSWSQ with QT_fp16): choose BH_STORAGE_*.
+ * Only on an empty index. */
+int bh_index_set_vector_storage(bh_index* h, int storage);
+int bh_index_get_vector_storage(const bh_index* h);
 
 /* -- the path: train / add / search ---------------------------------------------- */
 /* replaces faiss::IndexHNSW::train (a no-op for Flat storage; is_trained is true) */

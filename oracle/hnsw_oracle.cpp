@@ -79,15 +79,16 @@ inline float ip_native(const float* a, const float* b, int d) {
 }
 
 // Bit-exact emulation of the CUDA team reduction (see header comment).
+// CE = elements per 16-byte chunk of the stored vector: 4 for fp32 storage, 8 for fp16 storage.
 template <bool L2>
-inline float team_order(const float* a, const float* b, int d, int T) {
+inline float team_order(const float* a, const float* b, int d, int T, int CE = 4) {
     float lane[32];
-    const int nchunk = d / 4;
+    const int nchunk = d / CE;
     for (int j = 0; j < T; j++) {
         float acc = 0.f;
         for (int c = j; c < nchunk; c += T) {
-            for (int e = 0; e < 4; e++) {
-                float x = a[4 * c + e], y = b[4 * c + e];
+            for (int e = 0; e < CE; e++) {
+                float x = a[CE * c + e], y = b[CE * c + e];
                 if (L2) {
                     float t = x - y;
                     acc = std::fmaf(t, t, acc);
@@ -104,6 +105,40 @@ inline float team_order(const float* a, const float* b, int d, int T) {
         std::memcpy(lane, nxt, sizeof(float) * T);
     }
     return lane[0];
+}
+
+// Round to IEEE binary16 (round-to-nearest-even) and back, like __float2half_rn on the device.
+inline float round_to_half(float f) {
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    const uint32_t sign = x & 0x80000000u;
+    x &= 0x7FFFFFFFu;
+    float out;
+    if (x >= 0x7F800000u) {                    // inf / nan
+        out = f;
+        return out;
+    }
+    if (x >= 0x477FF000u) {                    // >= 65520: rounds to +-inf in fp16
+        uint32_t inf = sign | 0x7F800000u;
+        std::memcpy(&out, &inf, 4);
+        return out;
+    }
+    float a;
+    std::memcpy(&a, &x, 4);
+    if (x < 0x38800000u) {                     // subnormal in fp16: quantum 2^-24
+        const float q = 5.9604644775390625e-08f;
+        a = std::nearbyintf(a / q) * q;
+    } else {                                   // normal: keep 10 mantissa bits, RNE
+        const uint32_t lsb = (x >> 13) & 1u;
+        x += 0xFFFu + lsb;
+        x &= 0xFFFFE000u;
+        std::memcpy(&a, &x, 4);
+    }
+    uint32_t r;
+    std::memcpy(&r, &a, 4);
+    r |= sign;
+    std::memcpy(&out, &r, 4);
+    return out;
 }
 
 struct Oracle;
@@ -241,6 +276,7 @@ struct Oracle {
     int efConstruction = 40, efSearch = 16;  // A.1 defaults
     bool check_relative_distance = true;
     int team = 0;
+    bool half_storage = false;  // vectors rounded to IEEE fp16 on add (the engine's opt-in storage mode)
     std::vector<double> assign_probas;
     std::vector<int> cum_nneighbor_per_level;
     std::vector<int> levels;      // level+1 per vertex
@@ -306,9 +342,10 @@ struct Oracle {
 };
 
 inline float DistanceComputer::pair(const float* a, const float* b) const {
+    const int ce = o->half_storage ? 8 : 4;
     if (o->metric == METRIC_L2)
-        return o->team ? team_order<true>(a, b, o->d, o->team) : l2_native(a, b, o->d);
-    float s = o->team ? team_order<false>(a, b, o->d, o->team) : ip_native(a, b, o->d);
+        return o->team ? team_order<true>(a, b, o->d, o->team, ce) : l2_native(a, b, o->d);
+    float s = o->team ? team_order<false>(a, b, o->d, o->team, ce) : ip_native(a, b, o->d);
     return -s;  // NegativeDistanceComputer
 }
 inline float DistanceComputer::operator()(storage_idx_t i) const {
@@ -637,6 +674,14 @@ int orc_set_team(void* p, int T) {
     o->team = T;
     return 0;
 }
+// fp16 storage emulation: must be set before the first add/import; needs d % 8 == 0 in team mode
+int orc_set_half_storage(void* p, int on) {
+    Oracle* o = static_cast<Oracle*>(p);
+    if (o->ntotal != 0 || (on && o->d % 8 != 0)) return 1;
+    o->half_storage = on != 0;
+    return 0;
+}
+float orc_round_to_half(float f) { return round_to_half(f); }
 int64_t orc_ntotal(void* p) { return static_cast<Oracle*>(p)->ntotal; }
 int orc_entry_point(void* p) { return static_cast<Oracle*>(p)->entry_point; }
 int orc_max_level(void* p) { return static_cast<Oracle*>(p)->max_level; }
@@ -659,6 +704,8 @@ int orc_add(void* p, int64_t n, const float* x, int nthreads, int32_t* order_out
     if (n < 0) return 1;
     size_t n0 = (size_t)o->ntotal;
     o->xb.insert(o->xb.end(), x, x + (size_t)n * o->d);
+    if (o->half_storage)
+        for (size_t i = n0 * o->d; i < o->xb.size(); i++) o->xb[i] = round_to_half(o->xb[i]);
     o->ntotal += n;
     // The build reads vectors from o->xb (which may have been reallocated), so pass
     // the stored copy, not the caller's pointer.
@@ -739,6 +786,8 @@ int orc_import(void* p, int64_t n, const float* x, const int* levels, const int3
                int64_t nneigh, int entry_point, int max_level) {
     Oracle* o = static_cast<Oracle*>(p);
     o->xb.assign(x, x + (size_t)n * o->d);
+    if (o->half_storage)
+        for (float& v : o->xb) v = round_to_half(v);
     o->ntotal = n;
     o->levels.assign(levels, levels + n);
     o->offsets.assign(1, 0);

@@ -53,6 +53,10 @@ def _load(path: str | None = None) -> C.CDLL:
         getattr(L, name).argtypes = [C.c_void_p, C.c_int]
     L.orc_set_team.argtypes = [C.c_void_p, C.c_int]
     L.orc_set_team.restype = C.c_int
+    L.orc_set_half_storage.argtypes = [C.c_void_p, C.c_int]
+    L.orc_set_half_storage.restype = C.c_int
+    L.orc_round_to_half.argtypes = [C.c_float]
+    L.orc_round_to_half.restype = C.c_float
     L.orc_ntotal.argtypes = [C.c_void_p]
     L.orc_ntotal.restype = C.c_int64
     for name in ("orc_entry_point", "orc_max_level", "orc_n_levels_table"):
@@ -124,6 +128,11 @@ class OracleHNSWFlat:
     def set_team(self, T: int):
         if self._L.orc_set_team(self._h, int(T)) != 0:
             raise ValueError("bad team")
+
+    def set_half_storage(self, on: bool = True):
+        """Emulate the engine's opt-in fp16 vector storage (vectors rounded to binary16 on add)."""
+        if self._L.orc_set_half_storage(self._h, int(bool(on))) != 0:
+            raise ValueError("set_half_storage: index not empty or d % 8 != 0")
 
     def set_check_relative_distance(self, v: bool):
         self._L.orc_set_check_relative_distance(self._h, int(bool(v)))

@@ -141,3 +141,40 @@ def test_sequential_build_wide_rows_and_wide_vectors(oracle_mod, d, M, team, n):
     Do, Io = o.search(xq, 10, 64)
     D, I = idx.search(xq, 10, efSearch=64)
     assert np.array_equal(I, Io) and np.array_equal(D, Do)
+
+
+@pytest.mark.parametrize("d,M,team,metric", [(128, 16, 8, 1), (64, 8, 8, 0), (256, 8, 8, 1), (512, 8, 16, 1), (768, 8, 32, 0)])
+def test_fp16_storage_bit_exact_vs_oracle_half_mode(oracle_mod, d, M, team, metric):
+    """Opt-in fp16 vector storage: same algorithm on rows rounded to binary16 (fp32 accumulate).
+    The oracle's half-storage mode emulates it exactly: sequential build and search stay bit-equal,
+    reconstruct returns the rounded rows, and recall vs the fp32 ground truth stays high."""
+    import hnsw_b200
+    n = 1500
+    xb, xq = synthetic_dataset(d, n, 60, normalize=(metric == 0))
+    o = oracle_mod.OracleHNSWFlat(d, M, metric)
+    o.set_half_storage(True)
+    o.set_team(team)
+    o.efConstruction = 32
+    o.add(xb)
+    idx = hnsw_b200.IndexHNSWFlat(d, M, metric, storage="fp16")
+    idx.hnsw.efConstruction = 32
+    idx.set_build_params(max_batch=1)
+    idx.add(xb)
+    go, gg = o.export_graph(), idx.export_graph()
+    assert np.array_equal(gg["levels"], go["levels"])
+    mism = np.flatnonzero(gg["neighbors"] != go["neighbors"])
+    assert mism.size == 0, f"{mism.size} adjacency slots differ"
+    for ef in (16, 64):
+        Do, Io, So = o.search(xq, 10, ef, stats=True)
+        D, I, S = idx.search(xq, 10, efSearch=ef, stats=True, hash_bits=13)
+        assert np.array_equal(I, Io) and np.array_equal(D, Do) and np.array_equal(S, So)
+    assert np.array_equal(idx.reconstruct_n(0, 50), xb[:50].astype(np.float16).astype(np.float32))
+    _, gt = oracle_mod.brute_force_knn(xb, xq, 10, metric)
+    assert oracle_mod.recall_at_k(idx.search(xq, 10, efSearch=128)[1], gt) > 0.93
+    # batched build in fp16 mode: invariants hold
+    b = hnsw_b200.IndexHNSWFlat(d, M, metric, storage="fp16")
+    b.hnsw.efConstruction = 32
+    b.add(xb)
+    assert_graph_invariants(b.export_graph(), M, n)
+    with pytest.raises(RuntimeError):
+        hnsw_b200.IndexHNSWFlat(12, 4, 1, storage="fp16")      # d % 8 != 0
