@@ -373,8 +373,15 @@ def run_b200(a):
         idx.synchronize()
         barrier()
         gpu_launches = hnsw_b200.launch_count() - l0
+    ms_rank = ev0.elapsed_time(ev1) / a.steps
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     ms_step = ms_total / a.steps
+    ms_per_rank = [round(ms_rank, 4)]
+    if world > 1:
+        tt = torch.tensor([ms_rank], dtype=torch.float64, device=dev)
+        outl = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(outl, tt)
+        ms_per_rank = [round(float(x.item()), 4) for x in outl]
     value = world * a.nq / (ms_step * 1e-3)
     rec_timed = recall_at_k(I_d.cpu().numpy(), gt)
     rec_min = -max_over_ranks(-rec_timed)
@@ -509,6 +516,7 @@ def run_b200(a):
             "e2e": {"value": round(e2e, 1), "unit": "queries/s", "h2d_bytes_per_step": a.nq * a.d * 4,
                     "d2h_bytes_per_step": a.nq * a.k * 12},
             "gpu_launches": int(gpu_launches),
+            "ms_per_step_per_rank": ms_per_rank,
             "clocks": clk.summary(),
         }
         if sharded:
