@@ -337,6 +337,25 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     BH_CUDA(cudaSetDevice(h->device));
     const int64_t n0 = h->ntotal;
     const int d = h->d, M = h->M, deg0 = h->deg0();
+    // Everything that can reject the call is checked BEFORE the level RNG advances or any state
+    // changes, so a failed add() leaves the index exactly as it was.
+    const int efc = h->efConstruction;
+    if (efc < 1 || efc > 4096) return fail("efConstruction must be in [1, 4096]");
+    const int hb = h->auto_hash_bits(efc, h->bp.hash_bits);
+    if (bh::beam_group_smem(d, efc, hb, deg0) > h->smem_optin)
+        return fail("efConstruction/hash_bits need more shared memory than one SM has");
+    if (preset_levels)
+        for (int64_t i = 0; i < n; i++)
+            if (preset_levels[i] < 1 || preset_levels[i] > (int)h->assign_probas.size())
+                return fail("add: preset level out of range");
+    if (order_in) {
+        std::vector<char> seen(n, 0);
+        for (int64_t i = 0; i < n; i++) {
+            const int64_t r = (int64_t)order_in[i] - n0;
+            if (r < 0 || r >= n || seen[r]) return fail("add: order is not a permutation of the new ids");
+            seen[r] = 1;
+        }
+    }
     const bool dbg = getenv("BH_DEBUG_TIMING") != nullptr;
     auto t_prev = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) {
@@ -351,8 +370,6 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     std::vector<int32_t> new_levels(n);
     for (int64_t i = 0; i < n; i++) {
         if (preset_levels) {
-            if (preset_levels[i] < 1 || preset_levels[i] > (int)h->assign_probas.size())
-                return fail("add: preset level out of range");
             new_levels[i] = preset_levels[i];
         } else {
             new_levels[i] = h->random_level() + 1;
@@ -394,13 +411,7 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     // -- insertion order
     std::vector<int32_t> order;
     if (order_in) {
-        order.assign(order_in, order_in + n);
-        std::vector<char> seen(n, 0);
-        for (int64_t i = 0; i < n; i++) {
-            int64_t r = (int64_t)order[i] - n0;
-            if (r < 0 || r >= n || seen[r]) return fail("add: order is not a permutation of the new ids");
-            seen[r] = 1;
-        }
+        order.assign(order_in, order_in + n);  // validated above
     } else {
         faiss_insertion_order(h->levels, n0, n, order);
     }
@@ -462,11 +473,6 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     size_t max_items = 0;
     for (const Round& r : rounds) max_items = std::max(max_items, (size_t)(r.item_end - r.item_begin));
 
-    const int efc = h->efConstruction;
-    if (efc < 1 || efc > 4096) return fail("efConstruction must be in [1, 4096]");
-    const int hb = h->auto_hash_bits(efc, h->bp.hash_bits);
-    if (bh::beam_group_smem(d, efc, hb, deg0) > h->smem_optin)
-        return fail("efConstruction/hash_bits need more shared memory than one SM has");
 
     BH_CUDA(h->items_d.reserve(items.size(), h->stream));
     lap("  items alloc");

@@ -178,3 +178,23 @@ def test_fp16_storage_bit_exact_vs_oracle_half_mode(oracle_mod, d, M, team, metr
     assert_graph_invariants(b.export_graph(), M, n)
     with pytest.raises(RuntimeError):
         hnsw_b200.IndexHNSWFlat(12, 4, 1, storage="fp16")      # d % 8 != 0
+
+
+def test_rejected_add_leaves_index_untouched(oracle_mod):
+    """A rejected add() (bad order / bad preset level) must not advance the level RNG nor change
+    ntotal: the next add() still reproduces the oracle's graph."""
+    import hnsw_b200
+    xb, _ = synthetic_dataset(32, 700, 1)
+    o = oracle_mod.OracleHNSWFlat(32, 8)
+    o.set_team(8)
+    o.add(xb)
+    idx = hnsw_b200.IndexHNSWFlat(32, 8)
+    idx.set_build_params(max_batch=1)
+    with pytest.raises(RuntimeError):
+        idx.add(xb[:5], order=np.array([0, 1, 2, 3, 3], np.int32))
+    with pytest.raises(RuntimeError):
+        idx.add(xb[:5], levels=np.array([1, 1, 99, 1, 1], np.int32))
+    assert idx.ntotal == 0
+    idx.add(xb)
+    go, gg = o.export_graph(), idx.export_graph()
+    assert np.array_equal(gg["levels"], go["levels"]) and np.array_equal(gg["neighbors"], go["neighbors"])
