@@ -600,8 +600,7 @@ int bh_index_free(bh_index* h) {
     return 0;
 }
 
-int bh_index_reset(bh_index* h) {
-    if (!h) return fail("null index");
+static int reset_locked(bh_index* h) {
     BH_CUDA(cudaSetDevice(h->device));
     BH_CUDA(cudaStreamSynchronize(h->stream));
     h->levels.clear();
@@ -612,6 +611,12 @@ int bh_index_reset(bh_index* h) {
     h->max_level = -1;
     // faiss IndexHNSW::reset → hnsw.reset() keeps the RNG state; so do we.
     return 0;
+}
+
+int bh_index_reset(bh_index* h) {
+    if (!h) return fail("null index");
+    std::lock_guard<std::mutex> lk(h->mu);
+    return reset_locked(h);
 }
 
 int bh_index_set_vector_storage(bh_index* h, int storage) {
@@ -850,8 +855,8 @@ int bh_index_import_graph(bh_index* h, int64_t n, const float* x, const int32_t*
     if (n <= 0 || !x || !levels || !neighbors) return fail("import: bad arguments");
     if (n > (int64_t)INT32_MAX - 1) return fail("import: too many vectors");
     if (entry_point < 0 || entry_point >= n) return fail("import: entry point out of range");
+    std::lock_guard<std::mutex> lk(h->mu);
     BH_CUDA(cudaSetDevice(h->device));
-    if (int rc = bh_index_reset(h)) return rc;
     const int d = h->d, M = h->M, deg0 = h->deg0();
     std::vector<int32_t> ub(n);
     int64_t upper_rows = 0, need = 0;
@@ -876,6 +881,8 @@ int bh_index_import_graph(bh_index* h, int64_t n, const float* x, const int32_t*
         if (l0[i] < -1 || l0[i] >= n) return fail("import: neighbor id out of range");
     for (size_t i = 0; i < up.size(); i++)
         if (up[i] < -1 || up[i] >= n) return fail("import: neighbor id out of range");
+    // all checks passed: only now drop the old contents (a rejected import leaves the index as it was)
+    if (int rc = reset_locked(h)) return rc;
     if (int rc = h->ensure_capacity(n, upper_rows)) return rc;
     if (int rc = upload_vectors(h, 0, n, x)) return rc;
     BH_CUDA(cudaMemcpyAsync(h->nbr0.p, l0.data(), l0.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));

@@ -254,3 +254,18 @@ def test_id_selector_bitmap_matches_oracle(small_l2, frac):
             assert np.array_equal(S, So)
     with pytest.raises(RuntimeError):
         idx.search(small_l2["xq"], 10, sel_bitmap=bm[:100])          # bitmap too small
+
+
+def test_rejected_import_keeps_the_old_index(small_l2):
+    idx = _gpu_from_oracle(small_l2["oracle"], small_l2["xb"], 16)
+    g = small_l2["graph"]
+    D0, I0 = idx.search(small_l2["xq"], 10, efSearch=32)
+    bad = g["neighbors"].copy()
+    bad[5] = 10 ** 6                                   # neighbour id out of range
+    with pytest.raises(RuntimeError):
+        idx.import_graph(small_l2["xb"], g["levels"], bad, g["entry_point"], g["max_level"])
+    with pytest.raises(RuntimeError):
+        idx.import_graph(small_l2["xb"], g["levels"], g["neighbors"][:-3], g["entry_point"], g["max_level"])
+    assert idx.ntotal == 4000
+    D1, I1 = idx.search(small_l2["xq"], 10, efSearch=32)
+    assert np.array_equal(I1, I0) and np.array_equal(D1, D0)
