@@ -95,3 +95,60 @@ def test_sorted_list_formulation_equals_faiss_heaps(oracle_mod, seed):
     for i in range(len(xq)):
         ids, ndis, nhops = model_search(xb, g, cum, xq[i], 10, 32, True, 40 + 4 * M, member, dist)
         assert np.array_equal(ids, Io[i]) and nhops == So[i, 1]
+
+
+def _incremental_shrink(o, xb, owner, row, nver, src, max_size):
+    """DESIGN §3.3 in plain Python: row[:nver] is a verified (self-consistent) prefix; only pairs that
+    involve a special candidate (src or row[nver:]) are evaluated."""
+    d_to_owner = lambda v: np.float32(o.distance(xb[owner], xb[v]))
+    cands = [(d_to_owner(v), int(v)) for v in list(row) + [src]]
+    special = set(int(v) for v in row[nver:]) | {int(src)}
+    cands.sort()
+    kept, evals = [], 0
+    for dq, v in cands:
+        good = True
+        for _, u in kept:
+            if v in special or u in special:
+                evals += 1
+                if np.float32(o.distance(xb[u], xb[v])) < dq:
+                    good = False
+                    break
+        if good:
+            kept.append((dq, v))
+            if len(kept) >= max_size:
+                break
+    return [v for _, v in kept], evals
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_incremental_shrink_equals_full_heuristic(oracle_mod, seed):
+    rs = np.random.RandomState(seed)
+    d, n, deg = 24, 1500, 12
+    ran = with_appended = 0
+    xb, _ = synthetic_dataset(d, n, 1, seed=300 + seed)
+    o = oracle_mod.OracleHNSWFlat(d, 8)
+    o.add(xb[:50])                      # only used for distance() / shrink() on explicit candidate sets
+    o2 = oracle_mod.OracleHNSWFlat(d, 8)
+    o2.import_graph(xb, np.ones(n, np.int32), np.full(n * 16, -1, np.int32), 0, 0)  # vectors only
+    for trial in range(12):
+        owner = int(rs.randint(n))
+        pool = np.argsort(((xb - xb[owner]) ** 2).sum(1))[1:120]
+        # a verified prefix = output of one heuristic run on some candidate set
+        first = rs.choice(pool, 40, replace=False).astype(np.int32)
+        dq = np.array([o2.distance(xb[owner], xb[v]) for v in first], np.float32)
+        core = o2.shrink(first, dq, deg)                       # nearest-first, self-consistent
+        room = deg - len(core)
+        rest = [v for v in pool if v not in set(core.tolist())]
+        appended = rs.choice(rest, room, replace=False).astype(np.int32) if room > 0 else np.zeros(0, np.int32)  # fill the row
+        row = np.concatenate([core, appended]).astype(np.int32)
+        src = int(rs.choice([v for v in rest if v not in set(appended.tolist())]))
+        cand = np.concatenate([row, [src]]).astype(np.int32)
+        dqc = np.array([o2.distance(xb[owner], xb[v]) for v in cand], np.float32)
+        full = o2.shrink(cand, dqc, deg) if len(cand) >= deg else None
+        inc, evals = _incremental_shrink(o2, xb, owner, row, len(core), src, deg)
+        assert full is not None and len(cand) == deg + 1
+        assert inc == full.tolist(), (seed, trial)
+        assert evals <= (len(appended) + 1) * (len(cand))      # far fewer than the ~n^2/2 of a full run
+        ran += 1
+        with_appended += len(appended) > 0
+    assert ran == 12 and with_appended >= 1
