@@ -322,6 +322,10 @@ def run_b200(a):
     t_build = time.time() - t0
     build_launches = hnsw_b200.launch_count() - l0
     build_dev_s = idx.last_build_ms / 1e3
+    bc = idx.last_build_counters  # measured numerators of the build's HBM roofline
+    row_b = a.d * 4
+    build_bytes = ((bc["ndis0"] + bc["ndis_up"] + bc["sel_rows"] + bc["bl_rows"]) * row_b
+                   + bc["nhops0"] * 8 * a.M + bc["nhops_up"] * 4 * a.M + a.n * (row_b + 8 * a.M))
     t_build = max_over_ranks(t_build)
 
     # ---- efSearch sweep (untimed setup): recall, QPS, roofline fraction per ef
@@ -506,7 +510,12 @@ def run_b200(a):
                                     % round(sel["bytes_per_query"] * a.nq / 1e6)},
             "build_vectors_per_s": round(a.n / t_build, 1),
             "build": {"wall_s": round(t_build, 3), "device_s": round(build_dev_s, 3), "launches": build_launches,
-                      "vectors_per_s_device": round(a.n / build_dev_s, 1)},
+                      "vectors_per_s_device": round(a.n / build_dev_s, 1),
+                      "counters": bc, "bytes_per_vector": round(build_bytes / a.n),
+                      "roofline": {"bound": "hbm", "achieved": round(build_bytes / build_dev_s / 1e9, 1), "peak": peak,
+                                   "unit": "GB/s", "frac": round(build_bytes / build_dev_s / 1e9 / peak, 4),
+                                   "note": "algorithmic bytes: vectors scored by the insertion searches + candidate "
+                                           "vectors read by selection + vectors streamed by back-link shrinks + rows"}},
             "ef_sweep": sweep,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,

@@ -73,6 +73,7 @@ _SIGS = {
     "bh_index_synchronize": (C.c_int, [_P]),
     "bh_index_last_build_ms": (C.c_float, [_P]),
     "bh_index_last_search_ms": (C.c_float, [_P]),
+    "bh_index_last_build_counters": (C.c_int, [_P, _P]),
     "bh_launch_count": (C.c_int64, []),
     "bh_merge_topk_device": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int, _P, _P, _P, _P, _P, _P]),
     "bh_last_error": (C.c_char_p, []),

@@ -76,7 +76,15 @@ __global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, Bea
             if (t.items) {
                 unsigned long long* out = t.out_lists + (size_t)wi * t.ef;
                 for (int i = lane; i < lsize; i += 32) out[i] = key_clean(L[i]);
-                if (lane == 0) t.out_counts[wi] = lsize;
+                if (lane == 0) {
+                    t.out_counts[wi] = lsize;
+                    if (t.build_counters) {  // totals for the build's roofline (bench.py)
+                        atomicAdd(t.build_counters + 0, (unsigned long long)st.ndis0);
+                        atomicAdd(t.build_counters + 1, (unsigned long long)st.nhops0);
+                        atomicAdd(t.build_counters + 2, (unsigned long long)st.ndis_up);
+                        atomicAdd(t.build_counters + 3, (unsigned long long)st.nhops_up);
+                    }
+                }
             } else {
                 const float pad = g.is_l2 ? FLT_MAX : -FLT_MAX;
                 for (int i = lane; i < t.k; i += 32) {

@@ -287,7 +287,10 @@ __global__ void __launch_bounds__(64) select_and_link_kernel(GraphView g, BuildB
             kept = w.kept_key;
         }
         __syncwarp();
-        if (lane == 0) *nver_ptr(g, b, pt, level) = verified ? (uint8_t)K : (uint8_t)0;
+        if (lane == 0) {
+            *nver_ptr(g, b, pt, level) = verified ? (uint8_t)K : (uint8_t)0;
+            if (b.build_counters && verified) atomicAdd(b.build_counters + 4, (unsigned long long)n);  // candidate rows read
+        }
         // faiss pops link_targets farthest-first: row[i] = kept[K-1-i]
         for (int i = lane; i < g.deg0; i += 32) {
             const int e = item * g.deg0 + i;
@@ -410,6 +413,7 @@ __global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b,
                 q_loaded = true;
             }
             const int n = deg + 1;
+            if (lane == 0 && b.build_counters) atomicAdd(b.build_counters + 5, (unsigned long long)(n + 1));  // rows streamed (+ owner)
 #pragma unroll
             for (int i = 0; i < kMaxIdsPerLane; i++) {
                 const int idx = lane + 32 * i;

@@ -103,6 +103,8 @@ struct bh_index {
     int num_sms = 148;
     size_t smem_optin = 227 * 1024;
     DevBuf<int> counter;
+    DevBuf<unsigned long long> build_counters;  // [6], see bh_index_last_build_counters
+    unsigned long long last_build_counters[6] = {0, 0, 0, 0, 0, 0};
     // search staging
     mutable DevBuf<float> q_d, D_d;
     mutable DevBuf<int64_t> I_d;
@@ -231,7 +233,7 @@ struct bh_index {
     void free_all() {
         nver0.release(); nverU.release();
         vecs.release(); nbr0.release(); upper_base_d.release(); upper_nbr.release(); slot_head.release();
-        sel_d.release(); conv_d.release();
+        sel_d.release(); conv_d.release(); build_counters.release();
         counter.release(); q_d.release(); D_d.release(); I_d.release(); stats_d.release();
         items_d.release(); cand_lists.release(); cand_counts.release();
         e_slot.release(); e_src.release(); e_dst.release(); e_level.release(); e_next.release(); e_dist.release();
@@ -490,6 +492,8 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     BH_CUDA(h->e_next.reserve(max_edges, h->stream));
     BH_CUDA(h->e_dist.reserve(max_edges, h->stream));
 
+    BH_CUDA(h->build_counters.reserve(6, h->stream));
+    BH_CUDA(cudaMemsetAsync(h->build_counters.p, 0, 6 * sizeof(unsigned long long), h->stream));
     lap("scratch alloc + items H2D");
     BH_CUDA(cudaEventRecord(h->ev0, h->stream));
     for (const Round& r : rounds) {
@@ -506,6 +510,7 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
             t.max_steps = INT_MAX;
             t.hash_bits = hb;
             t.stats = nullptr;
+            t.build_counters = h->build_counters.p;
             t.counter = h->counter.p;
             BH_CUDA(cudaMemsetAsync(h->counter.p, 0, sizeof(int), h->stream));
             const int W = h->auto_warps(efc, hb, h->bp.warps_per_query, n_items);
@@ -527,6 +532,7 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
             b.nver0 = h->nver0.p;
             b.nverU = h->nverU.p;
             b.max_special = std::min(8, std::max(2, (16 * 1024) / (4 * h->row_floats())));
+            b.build_counters = h->build_counters.p;
             BH_CUDA(bh::launch_select_and_link(g, b, h->num_sms, h->stream));
             BH_CUDA(bh::launch_backlinks(g, b, h->num_sms, h->stream));
             bh::count_launch(3);
@@ -541,6 +547,8 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     BH_CUDA(cudaStreamSynchronize(h->stream));
     lap("wait for device");
     BH_CUDA(cudaEventElapsedTime(&h->last_build_ms, h->ev0, h->ev1));
+    BH_CUDA(cudaMemcpy(h->last_build_counters, h->build_counters.p, 6 * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -909,6 +917,11 @@ int bh_index_synchronize(const bh_index* h) {
     return 0;
 }
 float bh_index_last_build_ms(const bh_index* h) { return h ? h->last_build_ms : -1.f; }
+int bh_index_last_build_counters(const bh_index* h, uint64_t out[6]) {
+    if (!h || !out) return fail("null argument");
+    for (int i = 0; i < 6; i++) out[i] = h->last_build_counters[i];
+    return 0;
+}
 float bh_index_last_search_ms(const bh_index* h) { return h ? h->last_search_ms : -1.f; }
 
 int bh_merge_topk_device(int nshard, int64_t nq, int64_t k, int metric, const float* D_all,

@@ -26,6 +26,7 @@ struct BeamTask {
     int max_steps;  // nstep limit (INT_MAX = off)
     int hash_bits;
     int32_t* stats;  // device int32[n_items][4] or null
+    unsigned long long* build_counters;  // device [6] or null: {ndis0, nhops0, ndis_up, nhops_up, sel_rows, bl_rows}
     const uint8_t* sel;  // device IDSelectorBitmap over the shard's ids, or null (search mode only)
     int* counter;    // device work counter, zeroed before launch
 };
@@ -55,6 +56,7 @@ struct BuildBatch {
     uint8_t* nver0;           // [ntotal] level-0 rows
     uint8_t* nverU;           // [n_upper_rows]
     int max_special;          // cap on "unverified" candidates handled by the incremental shrink
+    unsigned long long* build_counters;  // device [6] or null (see BeamTask)
 };
 
 cudaError_t launch_select_and_link(const GraphView& g, const BuildBatch& b, int num_sms, cudaStream_t stream);

@@ -188,6 +188,13 @@ class IndexHNSWFlat:
         return float(_lib.lib().bh_index_last_build_ms(self._h))
 
     @property
+    def last_build_counters(self):
+        """Work counters of the last add(): ndis0, nhops0, ndis_up, nhops_up, sel_rows, bl_rows."""
+        out = np.zeros(6, np.uint64)
+        _lib.check(_lib.lib().bh_index_last_build_counters(self._h, out.ctypes.data))
+        return dict(zip(("ndis0", "nhops0", "ndis_up", "nhops_up", "sel_rows", "bl_rows"), (int(v) for v in out)))
+
+    @property
     def last_search_ms(self):
         return float(_lib.lib().bh_index_last_search_ms(self._h))
 

@@ -122,6 +122,10 @@ int bh_index_synchronize(const bh_index* h);
 /* device milliseconds of the most recent add() graph-construction phase / search launch */
 float bh_index_last_build_ms(const bh_index* h);
 float bh_index_last_search_ms(const bh_index* h);
+/* work counters of the most recent add(): {distance evaluations level 0, hops level 0, distance
+ * evaluations upper levels, hops upper levels, candidate vectors read by the selection heuristic,
+ * vectors streamed by back-link shrinks} — the numerators of the build's HBM roofline */
+int bh_index_last_build_counters(const bh_index* h, uint64_t out[6]);
 /* kernels launched by this library since load (for bench.py's gpu_launches) */
 int64_t bh_launch_count(void);
 
