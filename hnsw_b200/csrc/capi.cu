@@ -421,10 +421,10 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     // -- batch schedule. A round inserts points concurrently against the graph as it stood at the
     //    start of the round (faiss's OpenMP build has the same blindness between the points its
     //    threads are inserting at one moment). Rounds are kept small relative to the graph.
-    // auto: 8192 points per round, growing with the graph beyond 2M vertices (a round never exceeds
-    // 1/256 of the graph there), capped at 64k
+    // auto: 10240 points per round (~3 waves of resident insertion searches), growing with the graph
+    // beyond 2.6M vertices (a round never exceeds 1/256 of the graph there), capped at 64k
     const bool auto_batch = h->bp.max_batch <= 0;
-    const int max_batch = auto_batch ? 8192 : h->bp.max_batch;
+    const int max_batch = auto_batch ? 10240 : h->bp.max_batch;
     const int divisor = h->bp.batch_divisor > 0 ? h->bp.batch_divisor : 64;
     struct Round { int64_t item_begin, item_end; int new_entry, new_max_level; };
     std::vector<int4> items;
