@@ -425,7 +425,8 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     // beyond 2.6M vertices (a round never exceeds 1/256 of the graph there), capped at 64k
     const bool auto_batch = h->bp.max_batch <= 0;
     const int max_batch = auto_batch ? 10240 : h->bp.max_batch;
-    const int divisor = h->bp.batch_divisor > 0 ? h->bp.batch_divisor : 64;
+    const bool auto_div = h->bp.batch_divisor <= 0;
+    const int divisor = auto_div ? 64 : h->bp.batch_divisor;
     struct Round { int64_t item_begin, item_end; int new_entry, new_max_level; };
     std::vector<int4> items;
     std::vector<Round> rounds;
@@ -445,7 +446,11 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
         while (pos < n) {
             int64_t cap = max_batch;
             if (auto_batch) cap = std::min<int64_t>(65536, std::max<int64_t>(cap, in_graph / 256));
-            int64_t target = std::max<int64_t>(1, std::min<int64_t>(cap, in_graph / divisor));
+            // While the graph is below 1/32 of the size this call will reach, rounds may be coarser
+            // (1/16 of the graph): those vertices are <= 3 % of the final graph and their rows are
+            // reworked by the back-links of everything inserted later.
+            const int div_now = (auto_div && in_graph * 32 < n0 + n) ? std::min(divisor, 16) : divisor;
+            int64_t target = std::max<int64_t>(1, std::min<int64_t>(cap, in_graph / div_now));
             Round r{(int64_t)items.size(), 0, -1, -1};
             int64_t cnt = 0;
             while (pos < n && cnt < target) {
