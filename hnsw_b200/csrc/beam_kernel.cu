@@ -1,177 +1,13 @@
-// beam_kernel.cu — persistent traversal kernel (search mode and construction-search mode)
-// and its host-side dispatcher.
-//
-// One launch = one batch of queries (IndexHNSW::search's `omp parallel for` over queries,
-// SURVEY.md §3.1) or one batch of (point, level) insertion searches
-// (add_links_starting_from → search_neighbors_to_add, §3.2). Groups of W warps pull work
-// items from an atomic counter until the batch is drained.
+// beam_kernel.cu — dispatcher of the traversal kernel (see beam_kernel_impl.cuh).
 #include "beam.cuh"
 #include "engine.h"
 
-#include <cfloat>
-#include <climits>
-#include <cstdio>
-
 namespace bh {
 
-template <int TEAM, int CPL, int W, int R, int G, int MINB, bool HALF>
-__global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, BeamTask t) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int grp = warp / W;
-    const int wig = warp % W;
-    const int hash_slots = 1 << t.hash_bits;
-    const int rk = t.sel ? t.k : 0;
-    const size_t gbytes = group_smem_bytes(g.d, t.ef, hash_slots, g.deg0, rk);
-    const GroupSmem s = carve_group_smem(smem_raw + grp * gbytes, g.d, t.ef, hash_slots, g.deg0, rk);
-    Beam<TEAM, CPL, W, R, HALF> beam(g, s, wig, lane, 1 + grp);
-
-    if (wig == 0 && lane == 0) {
-        mbar_init(s.mbar, 1);
-        fence_mbar_init();
-    }
-    beam.group_sync();
-    uint32_t phase = 0;
-    const uint32_t qbytes_query = (uint32_t)g.d * 4u;             // fp32 query from the caller
-    const uint32_t qbytes_row = (uint32_t)g.nchunk * 16u;         // a stored row (fp32 or fp16)
-
-    for (;;) {
-        if (wig == 0 && lane == 0) s.ctrl[3] = atomicAdd(t.counter, 1);
-        beam.group_sync();
-        const int wi = s.ctrl[3];
-        if (wi >= t.n_items) break;
-
-        int level = 0, stop_level = 0;
-        const void* qsrc;
-        uint32_t qbytes = qbytes_query;
-        if (t.items) {  // construction: the query is the stored vector of the new point
-            const int4 it = __ldg(t.items + wi);
-            qsrc = reinterpret_cast<const char*>(g.vecs) + (size_t)it.x * qbytes_row;
-            qbytes = qbytes_row;
-            level = it.y;
-            stop_level = it.z;
-        } else {
-            qsrc = t.queries + (size_t)wi * g.d;
-        }
-        // query -> shared memory by 1-D bulk TMA, completion on the group's mbarrier
-        if (wig == 0 && lane == 0) {
-            fence_proxy_async();
-            mbar_expect_tx(s.mbar, qbytes);
-            tma_load_1d(s.qbuf, qsrc, qbytes, s.mbar);
-        }
-        mbar_wait(s.mbar, phase);
-        phase ^= 1;
-        beam.load_query_from_smem(t.items != nullptr);
-
-        BeamStats st;
-        uint32_t cur_id = 0;
-        float cur_d = 0.f;
-        beam.descend(stop_level, cur_id, cur_d, st);
-        beam.run(level, t.ef, t.ef_stop, t.max_steps, t.hash_bits, cur_id, cur_d, st, t.sel, rk);
-
-        if (wig == 0) {
-            const int lsize = t.sel ? s.ctrl[2] : s.ctrl[1];
-            const unsigned long long* L = t.sel ? s.rlist : s.list;
-            if (t.items) {
-                unsigned long long* out = t.out_lists + (size_t)wi * t.ef;
-                for (int i = lane; i < lsize; i += 32) out[i] = key_clean(L[i]);
-                if (lane == 0) {
-                    t.out_counts[wi] = lsize;
-                    if (t.build_counters) {  // totals for the build's roofline (bench.py)
-                        atomicAdd(t.build_counters + 0, (unsigned long long)st.ndis0);
-                        atomicAdd(t.build_counters + 1, (unsigned long long)st.nhops0);
-                        atomicAdd(t.build_counters + 2, (unsigned long long)st.ndis_up);
-                        atomicAdd(t.build_counters + 3, (unsigned long long)st.nhops_up);
-                    }
-                }
-            } else {
-                const float pad = g.is_l2 ? FLT_MAX : -FLT_MAX;
-                for (int i = lane; i < t.k; i += 32) {
-                    float dd = pad;
-                    int64_t id = -1;
-                    if (i < lsize) {
-                        dd = key_dist(L[i]);
-                        if (!g.is_l2) dd = -dd;
-                        id = (int64_t)key_id(L[i]);
-                    }
-                    t.D[(size_t)wi * t.k + i] = dd;
-                    t.I[(size_t)wi * t.k + i] = id;
-                }
-            }
-            if (t.stats && lane == 0) {
-#ifdef BH_PHASE_TIMING  // debug: overwrite {ndis_up, nhops_up} with phase cycles (gather, merge) per hop x16
-                const int h = st.nhops0 > 0 ? st.nhops0 : 1;
-                printf("q%d hops=%d ndis=%d cycles/hop: pop=%lld row=%lld hash=%lld (reset=%lld probe=%lld: ts0=%lld ts1=%lld rest=%lld maxtrips=%lld) gather=%lld merge=%lld\n",
-                       wi, st.nhops0, st.ndis0, st.t_pop / h, st.t_row / h, st.t_hash / h, st.t_reset / h, st.t_probe / h,
-                       st.t_ts0 / h, st.t_ts1 / h, st.t_rest / h, st.n_trips / h, st.t_gather / h, st.t_merge / h);
-#endif
-                int4 sv = make_int4(st.ndis0, st.nhops0, st.ndis_up, st.nhops_up);
-                reinterpret_cast<int4*>(t.stats)[wi] = sv;
-            }
-        }
-        beam.group_sync();
-    }
-}
-
-// ---------------------------------------------------------------- host dispatch
-namespace {
-
-template <int TEAM, int CPL, int W, int R, int G, int MINB, bool HALF>
-cudaError_t launch_one(const GraphView& g, const BeamTask& t, int num_sms, cudaStream_t stream,
-                       int* grid_out) {
-    auto kern = beam_kernel<TEAM, CPL, W, R, G, MINB, HALF>;
-    const size_t smem = (size_t)G * group_smem_bytes(g.d, t.ef, 1 << t.hash_bits, g.deg0, t.sel ? t.k : 0);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W * G, smem);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) return cudaErrorInvalidConfiguration;
-    long long groups_needed = ((long long)t.n_items + G - 1) / G;
-    long long grid = (long long)num_sms * occ;
-    if (grid > groups_needed) grid = groups_needed;
-    if (grid < 1) grid = 1;
-    if (grid_out) *grid_out = (int)grid;
-    kern<<<(unsigned)grid, 32 * W * G, smem, stream>>>(g, t);
-    return cudaGetLastError();
-}
-
-// variant (W == 1 only): 0 = R rows in flight per team, 4 blocks/SM (<=128 regs);
-// 1 = R/2 rows, 6 blocks/SM (<=80 regs); 2 = R/2 rows, 8 blocks/SM (<=64 regs);
-// 3 = R/2 rows, 5 blocks/SM (<=96 regs).
-template <int TEAM, int CPL, int R, bool HALF>
-cudaError_t launch_w(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
-                     cudaStream_t stream, int* grid_out) {
-    constexpr int RH = R >= 2 ? R / 2 : 1;
-    switch (W) {
-        case 1:
-            if (variant == 1) return launch_one<TEAM, CPL, 1, RH, 4, 6, HALF>(g, t, num_sms, stream, grid_out);
-            if (variant == 2) return launch_one<TEAM, CPL, 1, RH, 4, 8, HALF>(g, t, num_sms, stream, grid_out);
-            if (variant == 3) return launch_one<TEAM, CPL, 1, RH, 4, 5, HALF>(g, t, num_sms, stream, grid_out);
-            return launch_one<TEAM, CPL, 1, R, 4, 4, HALF>(g, t, num_sms, stream, grid_out);
-        case 2: return launch_one<TEAM, CPL, 2, R, 2, 1, HALF>(g, t, num_sms, stream, grid_out);
-        case 4: return launch_one<TEAM, CPL, 4, R, 1, 1, HALF>(g, t, num_sms, stream, grid_out);
-        case 8: return launch_one<TEAM, CPL, 8, R, 1, 1, HALF>(g, t, num_sms, stream, grid_out);
-        default: return cudaErrorInvalidValue;
-    }
-}
-
-// (TEAM, CPL) by the number of 16-byte chunks per stored row (fp32: d/4, fp16: d/8).
-template <bool HALF>
-cudaError_t launch_by_chunks(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
-                             cudaStream_t stream, int* grid_out) {
-    const int nc = g.nchunk;
-    if (nc <= 16) return launch_w<8, 2, 8, HALF>(g, t, W, variant, num_sms, stream, grid_out);  // 2 chunks/lane: 8 rows in flight
-    if (nc <= 32) return launch_w<8, 4, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out);
-    if (nc <= 64) return launch_w<16, 4, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out);
-    if (nc <= 128) return launch_w<32, 4, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out);
-    if (nc <= 256) return launch_w<32, 8, 2, HALF>(g, t, W, variant, num_sms, stream, grid_out);
-    if (nc <= 512) return launch_w<32, 16, 1, HALF>(g, t, W, variant, num_sms, stream, grid_out);
-    return cudaErrorInvalidValue;
-}
-
-}  // namespace
+cudaError_t launch_beam_f32(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
+                            cudaStream_t stream, int* grid_out);
+cudaError_t launch_beam_f16(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
+                            cudaStream_t stream, int* grid_out);
 
 size_t beam_group_smem(int d, int ef, int hash_bits, int deg, int rk) {
     return group_smem_bytes(d, ef, 1 << hash_bits, deg, rk);
@@ -179,8 +15,8 @@ size_t beam_group_smem(int d, int ef, int hash_bits, int deg, int rk) {
 
 cudaError_t launch_beam(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
                         cudaStream_t stream, int* grid_out) {
-    return g.half ? launch_by_chunks<true>(g, t, W, variant, num_sms, stream, grid_out)
-                  : launch_by_chunks<false>(g, t, W, variant, num_sms, stream, grid_out);
+    return g.half ? launch_beam_f16(g, t, W, variant, num_sms, stream, grid_out)
+                  : launch_beam_f32(g, t, W, variant, num_sms, stream, grid_out);
 }
 
 }  // namespace bh

@@ -870,7 +870,7 @@ int bh_index_import_graph(bh_index* h, int64_t n, const float* x, const int32_t*
     if (entry_point < 0 || entry_point >= n) return fail("import: entry point out of range");
     std::lock_guard<std::mutex> lk(h->mu);
     BH_CUDA(cudaSetDevice(h->device));
-    const int d = h->d, M = h->M, deg0 = h->deg0();
+    const int M = h->M, deg0 = h->deg0();
     std::vector<int32_t> ub(n);
     int64_t upper_rows = 0, need = 0;
     for (int64_t i = 0; i < n; i++) {
