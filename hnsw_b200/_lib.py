@@ -85,6 +85,11 @@ EXPORTED = tuple(_SIGS)
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
+        if not os.path.exists(LIB_PATH) and os.environ.get("BH_NO_AUTOBUILD") != "1":
+            try:  # the prebuilt library normally travels with the tree; compile it if it did not
+                build()
+            except Exception:
+                pass
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
