@@ -198,9 +198,10 @@ struct bh_index {
     int beam_variant(int ef, int hash_bits) const {
         const char* e = getenv("BH_BEAM_VARIANT");
         if (e) return atoi(e);
-        // rows of more than 128 chunks (2 KB) use 8-16 chunks per lane: the halved variants would keep
-        // a single row in flight per warp (measured at d=768: 0.88 vs 1.00 of the roof) -> full-R variant
-        if (row_floats() / 4 > 128) return 0;
+        // rows wider than 32 chunks (512 B) have fewer teams per warp, so the halved-R variants keep too
+        // few bytes in flight per warp (measured, ef=256: d=256 0.86 vs 0.92 of the roof, d=512 0.94 vs
+        // 1.01, d=768 0.88 vs 1.00) -> full-R, 128-register variant
+        if (row_floats() / 4 > 32) return 0;
         const size_t gs = bh::beam_group_smem(d, ef, hash_bits, deg0());
         if (24 * gs <= smem_optin - 6 * 1024) return 1;
         if (20 * gs <= smem_optin - 5 * 1024) return 3;  // 5 CTAs/SM, <=96 regs
