@@ -7,15 +7,19 @@
 //      closest unexpanded one, stop when none is left" — see DESIGN.md §3)
 // with the CPU structures replaced by:
 //   MinimaxHeap + result heap -> one sorted ef-list of 64-bit (dist,id) keys in shared
-//                                memory with an "expanded" bit, merged per hop by rank;
-//   VisitedTable              -> shared-memory open-addressing hash (atomicCAS, linear
-//                                probing). When it fills it is cleared and re-seeded with the
-//                                current list: vertices outside the list can then be re-scored,
-//                                but they were rejected against a threshold that only tightens,
-//                                so results are unchanged (only ndis grows);
+//                                memory with an "expanded" bit, merged in place once per hop
+//                                (rank + shift); with an IDSelector, a second k-entry list
+//                                holds the selector-filtered results;
+//   VisitedTable              -> shared-memory open-addressing hash read as 4-slot buckets
+//                                (one 128-bit load per probe step, one atomicCAS to claim a
+//                                slot). When it fills it is cleared and re-seeded with the
+//                                current list(s): vertices outside the list can then be
+//                                re-scored, but they were rejected against a threshold that only
+//                                tightens, so results are unchanged (only ndis grows);
 //   fvec_L2sqr / inner product-> TEAM lanes per vector, 128-bit gathers, R vectors in flight
 //                                per team, fixed fmaf order + xor-butterfly (bit-reproducible;
-//                                the oracle's team mode emulates it exactly).
+//                                the CPU checker's team mode emulates it exactly). Rows may be
+//                                stored as fp16 (HALF): chunks are widened exactly to fp32.
 #pragma once
 #include "common.cuh"
 
