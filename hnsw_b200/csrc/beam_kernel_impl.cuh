@@ -165,6 +165,7 @@ cudaError_t launch_by_chunks(const GraphView& g, const BeamTask& t, int W, int v
                              cudaStream_t stream, int* grid_out) {
     const int nc = g.nchunk;
     if (nc <= 16) return launch_w<8, 2, 8, HALF>(g, t, W, variant, num_sms, stream, grid_out);  // 2 chunks/lane: 8 rows in flight
+    if (nc == 24) return launch_w<8, 3, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out);  // d=96 fp32: exact fit
     if (nc <= 32) return launch_w<8, 4, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out);
     if (nc <= 64) return launch_w<16, 4, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out);
     if (nc <= 128) return launch_w<32, 4, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out);

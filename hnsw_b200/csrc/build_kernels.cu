@@ -559,6 +559,7 @@ cudaError_t dispatch_build_t(bool backlinks, const GraphView& g, const BuildBatc
                              cudaStream_t stream) {
     const int nc = g.nchunk;  // same (TEAM, CPL) table as the traversal kernel
     if (nc <= 16) return launch_build_pair<8, 2, HALF>(backlinks, g, b, num_sms, stream);
+    if (nc == 24) return launch_build_pair<8, 3, HALF>(backlinks, g, b, num_sms, stream);
     if (nc <= 32) return launch_build_pair<8, 4, HALF>(backlinks, g, b, num_sms, stream);
     if (nc <= 64) return launch_build_pair<16, 4, HALF>(backlinks, g, b, num_sms, stream);
     if (nc <= 128) return launch_build_pair<32, 4, HALF>(backlinks, g, b, num_sms, stream);
