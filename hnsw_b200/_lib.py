@@ -17,12 +17,13 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200_hnsw.h")
 class SearchParams(C.Structure):
     _fields_ = [("efSearch", C.c_int32), ("check_relative_distance", C.c_int32),
                 ("warps_per_query", C.c_int32), ("hash_bits", C.c_int32),
-                ("stats", C.c_void_p), ("sel_bitmap", C.c_void_p), ("sel_bitmap_bytes", C.c_int64)]
+                ("stats", C.c_void_p), ("sel_bitmap", C.c_void_p), ("sel_bitmap_bytes", C.c_int64),
+                ("visited_policy", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class BuildParams(C.Structure):
     _fields_ = [("max_batch", C.c_int32), ("batch_divisor", C.c_int32),
-                ("warps_per_query", C.c_int32), ("hash_bits", C.c_int32)]
+                ("warps_per_query", C.c_int32), ("hash_bits", C.c_int32), ("visited_policy", C.c_int32)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -10,12 +10,17 @@
 //                                memory with an "expanded" bit, merged in place once per hop
 //                                (rank + shift); with an IDSelector, a second k-entry list
 //                                holds the selector-filtered results;
-//   VisitedTable              -> shared-memory open-addressing hash read as 4-slot buckets
-//                                (one 128-bit load per probe step, one atomicCAS to claim a
-//                                slot). When it fills it is cleared and re-seeded with the
-//                                current list(s): vertices outside the list can then be
-//                                re-scored, but they were rejected against a threshold that only
-//                                tightens, so results are unchanged (only ndis grows);
+//   VisitedTable              -> a shared-memory table that may FORGET: a forgotten vertex can be
+//                                scored again, but it was rejected against a threshold that only
+//                                tightens — or it is still in the list and the merge drops the
+//                                identical key — so results are unchanged (only ndis grows).
+//                                Default policy (kVisitedAssoc16/32): set-associative, 16-byte
+//                                buckets read with one 128-bit load, FIFO eviction inside the
+//                                bucket, no global reset, no atomics; with 16-bit slots a bucket
+//                                holds eight quotiented ids (the bucket index is a bijective hash's
+//                                top bits, the slot keeps the rest), so 4 KB remember 2048 vertices.
+//                                kVisitedExact: open addressing over 32-bit slots, exact until 3/4
+//                                full (then cleared and re-seeded from the list) — the checker mode;
 //   fvec_L2sqr / inner product-> TEAM lanes per vector, 128-bit gathers, R vectors in flight
 //                                per team, fixed fmaf order + xor-butterfly (bit-reproducible;
 //                                the CPU checker's team mode emulates it exactly). Rows may be
@@ -253,6 +258,58 @@ struct Beam {
         __syncwarp();
     }
 
+    // Set-associative policy. `bbits` = log2(buckets). Returns true when `id` was not in its bucket
+    // (and records it, pushing the bucket's oldest entry out). No atomics: a lane reads its bucket,
+    // and if the id is absent writes the bucket back shifted by one entry with the id on top, then
+    // looks again. Two lanes racing on one bucket can only lose an insertion (that id is forgotten —
+    // harmless, see the header) — every slot always holds an id that WAS visited, so "visited" is
+    // never reported for a fresh vertex. (A row that names one vertex twice — never produced by a build —
+    // can make two lanes score it in the same hop; the merge drops the twin key.)
+    template <bool SLOT16>
+    __device__ __forceinline__ bool assoc_test_and_set(uint32_t id, int bbits) const {
+        uint32_t b, rem2 = 0, rem = 0;
+        if (SLOT16) {
+            // (id * odd) mod 2^(bbits+16) is a bijection on the id range, so (bucket, 16-bit remainder)
+            // names the id exactly; 0xFFFF marks an empty slot, and the one id per bucket whose
+            // remainder is 0xFFFF is simply never remembered.
+            const uint32_t h = (id * 2654435761u) & ((1u << (bbits + 16)) - 1u);
+            b = h >> 16;
+            rem = h & 0xFFFFu;
+            if (rem == 0xFFFFu) return true;
+            rem2 = rem | (rem << 16);
+        } else {
+            b = hash_id(id, bbits);
+        }
+        bool fresh = false;
+        for (;;) {
+            const uint4 v = lds128_volatile(s.hash + 4 * b);
+            bool found;
+            if (SLOT16) {  // "some 16-bit half of v ^ rem2 is zero", the classic has-zero test per word
+                const uint32_t x0 = v.x ^ rem2, x1 = v.y ^ rem2, x2 = v.z ^ rem2, x3 = v.w ^ rem2;
+                const uint32_t c = 0x00010001u;
+                found = ((((x0 - c) & ~x0) | ((x1 - c) & ~x1) | ((x2 - c) & ~x2) | ((x3 - c) & ~x3)) & 0x80008000u) != 0u;
+            } else
+                found = v.x == id || v.y == id || v.z == id || v.w == id;
+            if (found) return fresh;
+            uint4 n;
+            if (SLOT16) {
+                n.x = __funnelshift_r(v.x, v.y, 16);
+                n.y = __funnelshift_r(v.y, v.z, 16);
+                n.z = __funnelshift_r(v.z, v.w, 16);
+                n.w = (v.w >> 16) | (rem << 16);
+            } else {
+                n = make_uint4(v.y, v.z, v.w, id);
+            }
+            sts128_volatile(s.hash + 4 * b, n);
+            fresh = true;
+        }
+    }
+    __device__ __forceinline__ bool visited_test_and_set(uint32_t id, int mode, int bits) const {
+        if (mode == kVisitedAssoc16) return assoc_test_and_set<true>(id, bits - 2);
+        if (mode == kVisitedAssoc32) return assoc_test_and_set<false>(id, bits - 2);
+        return hash_test_and_set(id, bits);
+    }
+
     // ---- App. A.4: greedy descent from (cur_id) at levels max_level .. stop_level+1 ----
     // All warps of the group call this; on return the leader's (cur_id, cur_d) are valid.
     __device__ void descend(int stop_level, uint32_t& cur_id, float& cur_d, BeamStats& st) const {
@@ -329,15 +386,15 @@ struct Beam {
     // On return ctrl[1] = list size.
     // sel/rk: faiss IDSelectorBitmap and the k of the selector-filtered result list (nullptr/0: none).
     //          The selector decides only what enters the RESULT list; traversal is unchanged.
-    __device__ void run(int level, int ef, int ef_stop, int max_steps, int hash_bits, uint32_t start_id,
+    __device__ void run(int level, int ef, int ef_stop, int max_steps, int vmode, int hash_bits, uint32_t start_id,
                         float start_d, BeamStats& st, const uint8_t* sel = nullptr, int rk = 0) const {
         int lsize = 0, cursor = 0, hcount = 0, nstep = 0, rsize = 0, rcursor = 0;
-        const int hlimit = (3 << hash_bits) >> 2;  // reset above 75 % load
+        const int hlimit = (3 << hash_bits) >> 2;  // kVisitedExact: reset above 75 % load
         if (wig == 0) {
             hash_clear(hash_bits);
             if (lane == 0) {
                 s.list[0] = pack_key(start_d, start_id);
-                hash_test_and_set(start_id, hash_bits);
+                visited_test_and_set(start_id, vmode, hash_bits);
             }
             lsize = 1;
             hcount = 1;
@@ -375,8 +432,11 @@ struct Beam {
                     BH_T(t2);
                     BH_ACC(t_row, t1, t2);
                     BH_T(t2a);
-                    if (hcount + (level == 0 ? g.deg0 : g.degU) > hlimit) {  // forget-and-reseed (see header)
+                    if (vmode == kVisitedExact && hcount + (level == 0 ? g.deg0 : g.degU) > hlimit) {  // forget-and-reseed (see header)
                         hash_clear(hash_bits);
+#ifdef BH_PHASE_TIMING
+                        st.n_reset++;
+#endif
                         for (int i = lane; i < lsize; i += 32) hash_test_and_set(key_id(L[i]), hash_bits);
                         hcount = lsize;
                         if (sel) {  // results outside the list must stay "visited" too, or they could re-enter twice
@@ -394,7 +454,7 @@ struct Beam {
                     n_new = 0;
 #pragma unroll
                     for (int i = 0; i < kMaxIdsPerLane; i++) {
-                        const bool isnew = ids[i] >= 0 && hash_test_and_set((uint32_t)ids[i], hash_bits);
+                        const bool isnew = ids[i] >= 0 && visited_test_and_set((uint32_t)ids[i], vmode, hash_bits);
                         const unsigned bal = __ballot_sync(0xffffffffu, isnew);
                         if (isnew) s.cand_id[n_new + __popc(bal & ((1u << lane) - 1u))] = ids[i];
                         n_new += __popc(bal);
@@ -466,19 +526,50 @@ struct Beam {
         if (n_acc == 0) return;
         __syncwarp();
         int* acc_pos = s.cand_id;  // free again: the hop's ids have been scored
-        int minpos = ef;
-        for (int a = lane; a < n_acc; a += 32) {
-            const unsigned long long ka = s.acc_key[a];
-            int ra = 0;
-            for (int b2 = 0; b2 < n_acc; b2++) ra += s.acc_key[b2] < ka;
-            int lo = 0, hi = lsize;  // lower_bound on clean keys
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (key_clean(L[mid]) < ka) lo = mid + 1; else hi = mid;
+        int minpos;
+        for (;;) {
+            minpos = ef;
+            bool dup = false;
+            for (int a0 = 0; a0 < n_acc; a0 += 32) {
+                const int a = a0 + lane;
+                if (a < n_acc) {
+                    const unsigned long long ka = s.acc_key[a];
+                    int ra = 0;
+                    bool twin = false;  // the same key earlier in this batch (a row that names a vertex twice)
+                    for (int b2 = 0; b2 < n_acc; b2++) {
+                        const unsigned long long kb = s.acc_key[b2];
+                        ra += kb < ka;
+                        twin |= kb == ka && b2 < a;
+                    }
+                    int lo = 0, hi = lsize;  // lower_bound on clean keys
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (key_clean(L[mid]) < ka) lo = mid + 1; else hi = mid;
+                    }
+                    // the identical (distance, id) key is already listed: a vertex the visited table
+                    // forgot was scored again — it must not enter twice
+                    if (twin || (lo < lsize && key_clean(L[lo]) == ka)) dup = true, s.acc_key[a] = ~0ull;
+                    const int pos = ra + lo;
+                    acc_pos[a] = pos;
+                    minpos = pos < minpos ? pos : minpos;
+                }
             }
-            const int pos = ra + lo;
-            acc_pos[a] = pos;
-            minpos = pos < minpos ? pos : minpos;
+            if (!__any_sync(0xffffffffu, dup)) break;
+            // rare: squeeze the dropped keys out of acc_key (in place, front to back) and rank again
+            __syncwarp();
+            int m = 0;
+            for (int a0 = 0; a0 < n_acc; a0 += 32) {
+                const int a = a0 + lane;
+                const unsigned long long ka = a < n_acc ? s.acc_key[a] : ~0ull;
+                const bool keep = ka != ~0ull;
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                __syncwarp();
+                if (keep) s.acc_key[m + __popc(bal & ((1u << lane) - 1u))] = ka;
+                m += __popc(bal);
+                __syncwarp();
+            }
+            n_acc = m;
+            if (n_acc == 0) return;
         }
         minpos = __reduce_min_sync(0xffffffffu, minpos);  // REDUX: one instruction
         __syncwarp();

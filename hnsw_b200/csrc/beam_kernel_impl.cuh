@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, Bea
         uint32_t cur_id = 0;
         float cur_d = 0.f;
         beam.descend(stop_level, cur_id, cur_d, st);
-        beam.run(level, t.ef, t.ef_stop, t.max_steps, t.hash_bits, cur_id, cur_d, st, t.sel, rk);
+        beam.run(level, t.ef, t.ef_stop, t.max_steps, t.visited_mode, t.hash_bits, cur_id, cur_d, st, t.sel, rk);
 
         if (wig == 0) {
             const int lsize = t.sel ? s.ctrl[2] : s.ctrl[1];
@@ -102,11 +102,12 @@ __global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, Bea
                 }
             }
             if (t.stats && lane == 0) {
-#ifdef BH_PHASE_TIMING  // debug: overwrite {ndis_up, nhops_up} with phase cycles (gather, merge) per hop x16
+#ifdef BH_PHASE_TIMING  // debug builds only (scripts/phase_timing.py): SM cycles per hop, by phase
                 const int h = st.nhops0 > 0 ? st.nhops0 : 1;
-                printf("q%d hops=%d ndis=%d cycles/hop: pop=%lld row=%lld hash=%lld (reset=%lld probe=%lld: ts0=%lld ts1=%lld rest=%lld maxtrips=%lld) gather=%lld merge=%lld\n",
-                       wi, st.nhops0, st.ndis0, st.t_pop / h, st.t_row / h, st.t_hash / h, st.t_reset / h, st.t_probe / h,
-                       st.t_ts0 / h, st.t_ts1 / h, st.t_rest / h, st.n_trips / h, st.t_gather / h, st.t_merge / h);
+                printf("q%d hops=%d ndis=%d resets=%d cycles/hop: pop=%lld row=%lld hash=%lld (reset=%lld probe=%lld) "
+                       "gather=%lld merge=%lld\n",
+                       wi, st.nhops0, st.ndis0, st.n_reset, st.t_pop / h, st.t_row / h, st.t_hash / h, st.t_reset / h,
+                       st.t_probe / h, st.t_gather / h, st.t_merge / h);
 #endif
                 int4 sv = make_int4(st.ndis0, st.nhops0, st.ndis_up, st.nhops_up);
                 reinterpret_cast<int4*>(t.stats)[wi] = sv;

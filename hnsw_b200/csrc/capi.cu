@@ -13,7 +13,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <random>
 #include <string>
 #include <vector>
@@ -53,9 +56,11 @@ struct DevBuf {
         if (e != cudaSuccess) return e;
         if (keep && p && keep_n) {
             e = cudaMemcpyAsync(np, p, keep_n * sizeof(T), cudaMemcpyDeviceToDevice, s);
-            if (e != cudaSuccess) return e;
-            e = cudaStreamSynchronize(s);
-            if (e != cudaSuccess) return e;
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) {
+                cudaFree(np);
+                return e;
+            }
         }
         if (p) cudaFree(p);
         p = np;
@@ -69,6 +74,92 @@ struct DevBuf {
     }
 };
 
+// Page-locked, device-mapped host buffer (staging for pageable callers; the kernels read / write it
+// directly over PCIe, see bh_index_search).
+template <class T>
+struct PinBuf {
+    T* p = nullptr;
+    T* dev = nullptr;  // the same memory as the device sees it
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        release();
+        cudaError_t e = cudaHostAlloc((void**)&p, n * sizeof(T), cudaHostAllocPortable | cudaHostAllocMapped);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return e;
+        }
+        e = cudaHostGetDevicePointer((void**)&dev, p, 0);
+        if (e != cudaSuccess) {
+            release();
+            return e;
+        }
+        cap = n;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        dev = nullptr;
+        cap = 0;
+    }
+};
+
+// Resources of one in-flight search call. An index keeps a small pool of these, so concurrent
+// bh_index_search calls on one handle run side by side (faiss: `search` is const and thread-safe).
+// A context has kLanes streams: a pageable host batch is cut into chunks that go round-robin over
+// the lanes, so staging chunk i+1 on the CPU overlaps the traversal of chunk i, and the chunks'
+// kernels overlap each other's tails.
+constexpr int kLanes = 3;
+constexpr int kMaxSearchCtx = 8;
+struct SearchLane {
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t done = nullptr;
+    PinBuf<float> hq, hD;
+    PinBuf<int64_t> hI;
+    PinBuf<int32_t> hS;
+    int64_t pending_i0 = -1, pending_m = 0;  // chunk whose results sit in hD/hI (not yet copied out)
+};
+struct SearchCtx {
+    SearchLane lane[kLanes];
+    DevBuf<int> counters;    // one work counter per lane
+    DevBuf<float> q_d;       // re-aligned / zero-padded queries of a *_device call
+    DevBuf<uint8_t> sel_d;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool busy = false;
+    cudaError_t init(cudaStream_t primary) {
+        cudaError_t e;
+        for (int i = 0; i < kLanes; i++) {
+            if (i == 0 && primary) {
+                lane[i].stream = primary;
+            } else {
+                if ((e = cudaStreamCreateWithFlags(&lane[i].stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+                lane[i].own_stream = true;
+            }
+            if ((e = cudaEventCreateWithFlags(&lane[i].done, cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+        if ((e = cudaEventCreate(&ev0)) != cudaSuccess) return e;
+        if ((e = cudaEventCreate(&ev1)) != cudaSuccess) return e;
+        return counters.reserve(kLanes, lane[0].stream);
+    }
+    void destroy() {
+        for (int i = 0; i < kLanes; i++) {
+            SearchLane& l = lane[i];
+            if (l.stream) cudaStreamSynchronize(l.stream);
+            l.hq.release(); l.hD.release(); l.hI.release(); l.hS.release();
+            if (l.done) cudaEventDestroy(l.done);
+            if (l.own_stream && l.stream) cudaStreamDestroy(l.stream);
+            l.stream = nullptr;
+            l.done = nullptr;
+        }
+        counters.release(); q_d.release(); sel_d.release();
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        ev0 = ev1 = nullptr;
+    }
+};
+
 int ceil_log2(long long v) {
     int b = 0;
     while ((1ll << b) < v) b++;
@@ -78,12 +169,21 @@ int ceil_log2(long long v) {
 }  // namespace
 
 struct bh_index {
-    int d = 0, M = 0, metric = BH_METRIC_L2, device = 0;
+    int d = 0;   // the caller's dimension (faiss index.d)
+    int dp = 0;  // stored row width in elements: d rounded up to a whole number of 16-byte chunks (4 fp32 /
+                 // 8 fp16), the tail zero-filled — adds exact zeros to L2 and IP, so distances are unchanged
+    int M = 0, metric = BH_METRIC_L2, device = 0;
     int storage = BH_STORAGE_F32;  // BH_STORAGE_F16: rows held as fp16 (opt-in)
     int efSearch = 16, efConstruction = 40;  // faiss HNSW defaults (App. A.1)
     bool check_relative_distance = true;
-    bh_build_params bp{0, 0, 0, 0};
-    mutable std::mutex mu;  // one operation at a time per handle (stream, counter and staging are shared)
+    bh_build_params bp{0, 0, 0, 0, 0};
+    // add / reset / import hold `rw` exclusively; searches, reconstruct and export share it (faiss: search
+    // is const and may run concurrently, add must not overlap anything). Each search call works in a
+    // SearchCtx taken from `pool`.
+    mutable std::shared_mutex rw;
+    mutable std::mutex pool_mu;
+    mutable std::condition_variable pool_cv;
+    mutable std::vector<std::unique_ptr<SearchCtx>> pool;
     std::vector<double> assign_probas;
     std::vector<int> cum_nn;
     std::mt19937 rng{12345};
@@ -98,6 +198,7 @@ struct bh_index {
     DevBuf<int32_t> nbr0, upper_base_d, upper_nbr, slot_head;
     DevBuf<uint8_t> nver0, nverU;  // verified prefix per adjacency row (build_kernels.cu)
     int64_t slot_level0 = 0;  // slot numbering base used when slot_head was laid out
+    int64_t row_cap = 0, upper_row_cap = 0;  // rows every per-row / per-upper-row buffer can hold
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int num_sms = 148;
@@ -105,12 +206,7 @@ struct bh_index {
     DevBuf<int> counter;
     DevBuf<unsigned long long> build_counters;  // [6], see bh_index_last_build_counters
     unsigned long long last_build_counters[6] = {0, 0, 0, 0, 0, 0};
-    // search staging
-    mutable DevBuf<float> q_d, D_d;
-    mutable DevBuf<int64_t> I_d;
-    mutable DevBuf<int32_t> stats_d;
-    mutable DevBuf<uint8_t> sel_d;
-    mutable float last_search_ms = 0.f;
+    mutable std::atomic<float> last_search_ms{0.f};
     float last_build_ms = 0.f;
     // build scratch
     DevBuf<int4> items_d;
@@ -120,8 +216,10 @@ struct bh_index {
 
     int deg0() const { return 2 * M; }
     bool half() const { return storage == BH_STORAGE_F16; }
-    int row_floats() const { return half() ? d / 2 : d; }  // stored row size in 4-byte units
+    int row_floats() const { return half() ? dp / 2 : dp; }  // stored row size in 4-byte units
+    void set_padded_dim() { dp = half() ? (d + 7) / 8 * 8 : (d + 3) / 4 * 4; }
     mutable DevBuf<float> conv_d;                           // fp32 staging for fp16 conversion
+    mutable std::mutex conv_mu;                             // reconstruct_n calls may overlap
 
     bh::GraphView view() const {
         bh::GraphView g;
@@ -129,7 +227,7 @@ struct bh_index {
         g.nbr0 = nbr0.p;
         g.upper_base = upper_base_d.p;
         g.upper_nbr = upper_nbr.p;
-        g.d = d;
+        g.d = dp;
         g.nchunk = row_floats() / 4;
         g.half = half() ? 1 : 0;
         g.deg0 = deg0();
@@ -163,17 +261,37 @@ struct bh_index {
         return (int)assign_probas.size() - 1;
     }
 
-    // Visited-hash slots per query. The table is "forgetful" (beam.cuh), so its size is a pure
-    // performance knob: small tables keep many queries resident per SM at the price of a few
-    // re-scored vertices. Minimum: 3/4 of the slots must hold the ef-list plus one full row.
+    // Visited table per query (beam.cuh). Every policy may forget without changing results, so the
+    // size is a pure performance knob: bytes of shared memory per resident query against re-scored
+    // vertices. Default = set-associative with 16-bit quotient slots: measured by replaying the
+    // traversal on a 1M x 128 graph (scripts/visited_policy_sim.py), 32 remembered vertices per list
+    // entry (4 buckets x 8 ways x ef) keep the re-scored fraction at 2-3 % for ef 16..512, against
+    // 12-32 % for the round-1 clear-and-re-seed table of the same bytes.
+    //   policy 0 (auto): req_bits == 0 -> set-associative, auto size; req_bits > 0 -> exact table of
+    //                    2^req_bits slots (the checker mode: exact while it does not fill)
+    //   policy 1: exact / clear-and-re-seed;  policy 2: set-associative (4 << req_bits bytes)
     int min_hash_bits(int ef) const { return std::max(8, ceil_log2(((long long)(ef + deg0()) * 4 + 2) / 3 + 1)); }
-    int auto_hash_bits(int ef, int req) const {
-        const int lo = min_hash_bits(ef);
-        if (req > 0) return std::min(std::max(req, lo), 16);
-        // measured on 1M x 128 (profiles/README.md): ~4 slots per list entry is the sweet spot
-        int b = std::min(ceil_log2((long long)ef * 4), 10);
-        b = std::max(b, 9);
-        return std::min(std::max(b, lo), 15);
+    void pick_visited(int ef, int policy, int req_bits, int& mode, int& bits) const {
+        const bool exact = policy == 1 || (policy == 0 && req_bits > 0);
+        if (exact) {
+            mode = bh::kVisitedExact;
+            const int lo = min_hash_bits(ef);  // 3/4 of the slots must hold the ef-list plus one full row
+            if (req_bits > 0) {
+                bits = std::min(std::max(req_bits, lo), 16);
+            } else {
+                int b = std::min(ceil_log2((long long)ef * 4), 10);
+                bits = std::min(std::max(std::max(b, 9), lo), 15);
+            }
+            return;
+        }
+        if (req_bits > 0) {
+            bits = std::min(std::max(req_bits, 4), 15);
+        } else {
+            const char* e = getenv("BH_VISITED_BITS");  // experiments only
+            bits = e ? atoi(e) : std::min(std::max(ceil_log2((long long)ef * 4) + 2, 8), 12);
+        }
+        // 16-bit slots name an id exactly only while ntotal <= buckets * 2^16
+        mode = (ntotal <= (1ll << (bits + 14))) ? bh::kVisitedAssoc16 : bh::kVisitedAssoc32;
     }
     // Warps cooperating on one query. With enough work items to fill the GPU, one warp per query
     // keeps the most queries in flight (throughput regime). With few items (small query batches,
@@ -181,7 +299,7 @@ struct bh_index {
     // W warps score a hop's ~50 vectors in one gather round instead of 3-6 serial ones.
     int auto_warps(int ef, int hash_bits, int req, long long n_items) const {
         if (req == 1 || req == 2 || req == 4 || req == 8) return req;
-        const size_t s = bh::beam_group_smem(d, ef, hash_bits, deg0());
+        const size_t s = bh::beam_group_smem(dp, ef, hash_bits, deg0());
         // measured on an idle B200 (scripts/small_batch.py): 11 us/hop at W=1, 6.5-7 us at W=4;
         // W=8 never wins, and beyond ~1k items W=1's higher residency wins.
         int w = 1;
@@ -191,6 +309,15 @@ struct bh_index {
         if (w == 1 && 4 * s > smem_optin) w = 2;
         if (w == 2 && 2 * s > smem_optin) w = 4;
         return w;
+    }
+    // auto_warps, then widened (W -> 2W: half as many query groups per CTA) until the CTA's groups fit in
+    // shared memory. False when even one group per CTA does not fit.
+    bool pick_warps(int ef, int hb, int rk, int req, long long n_items, int& W) const {
+        W = auto_warps(ef + rk, hb, req, n_items);
+        const size_t gs = bh::beam_group_smem(dp, ef, hb, deg0(), rk);
+        auto groups = [](int w) { return w >= 4 ? 1 : 4 / w; };
+        while ((size_t)groups(W) * gs > smem_optin && W < 4) W *= 2;
+        return (size_t)groups(W) * gs <= smem_optin;
     }
     // Register/occupancy variant of the one-warp-per-query kernel (beam_kernel.cu): 1 = 80 regs,
     // 6 CTAs/SM, used while 24 queries' state fits in one SM's shared memory; then 3 = 96 regs, 5 CTAs;
@@ -202,34 +329,37 @@ struct bh_index {
         // few bytes in flight per warp (measured, ef=256: d=256 0.86 vs 0.92 of the roof, d=512 0.94 vs
         // 1.01, d=768 0.88 vs 1.00) -> full-R, 128-register variant
         if (row_floats() / 4 > 32) return 0;
-        const size_t gs = bh::beam_group_smem(d, ef, hash_bits, deg0());
+        const size_t gs = bh::beam_group_smem(dp, ef, hash_bits, deg0());
         if (24 * gs <= smem_optin - 6 * 1024) return 1;
         if (20 * gs <= smem_optin - 5 * 1024) return 3;  // 5 CTAs/SM, <=96 regs
         return 0;
     }
 
+    // Row capacity is committed (row_cap) only after EVERY per-row buffer has reached it, and each
+    // buffer is checked on its own (DevBuf::reserve is a no-op when large enough): an allocation
+    // failure half-way leaves row_cap at the old value, so the next add() retries the buffers that
+    // are still short instead of trusting the ones that already grew.
     int ensure_capacity(int64_t n_new_total, int64_t upper_rows_total) {
         const int64_t old_n = ntotal;
         const int rf = row_floats();
-        if ((size_t)n_new_total > (size_t)(vecs.cap / rf)) {
-            int64_t cap = std::max<int64_t>(n_new_total, (int64_t)(vecs.cap / rf) * 3 / 2);
-            BH_CUDA(vecs.reserve((size_t)cap * rf, stream, true, (size_t)old_n * rf));
-            BH_CUDA(nbr0.reserve((size_t)cap * deg0(), stream, true, (size_t)old_n * deg0()));
-            BH_CUDA(upper_base_d.reserve((size_t)cap, stream, true, (size_t)old_n));
-            BH_CUDA(nver0.reserve((size_t)cap, stream, true, (size_t)old_n));
-        }
-        if ((size_t)upper_rows_total * M > upper_nbr.cap) {
-            size_t cap = std::max<size_t>((size_t)upper_rows_total * M, upper_nbr.cap * 3 / 2);
-            BH_CUDA(upper_nbr.reserve(cap, stream, true, (size_t)n_upper_rows * M));
-            BH_CUDA(nverU.reserve(cap / M + 1, stream, true, (size_t)n_upper_rows));
-        }
+        int64_t want = row_cap;
+        if (n_new_total > row_cap) want = std::max<int64_t>(n_new_total, row_cap * 3 / 2);
+        BH_CUDA(vecs.reserve((size_t)want * rf, stream, true, (size_t)old_n * rf));
+        BH_CUDA(nbr0.reserve((size_t)want * deg0(), stream, true, (size_t)old_n * deg0()));
+        BH_CUDA(upper_base_d.reserve((size_t)want, stream, true, (size_t)old_n));
+        BH_CUDA(nver0.reserve((size_t)want, stream, true, (size_t)old_n));
+        row_cap = want;
+        int64_t want_up = upper_row_cap;
+        if (upper_rows_total > upper_row_cap) want_up = std::max<int64_t>(upper_rows_total, upper_row_cap * 3 / 2);
+        BH_CUDA(upper_nbr.reserve((size_t)want_up * M, stream, true, (size_t)n_upper_rows * M));
+        BH_CUDA(nverU.reserve((size_t)want_up + 1, stream, true, (size_t)n_upper_rows));
+        upper_row_cap = want_up;
         // pending-list heads: one per adjacency row, all -1 between batches
-        const int64_t level0_rows = (int64_t)(vecs.cap / row_floats());
-        const size_t need = (size_t)level0_rows + upper_nbr.cap / M + 1;
-        if (need > slot_head.cap || level0_rows != slot_level0) {
+        const size_t need = (size_t)row_cap + (size_t)upper_row_cap + 1;
+        if (need > slot_head.cap || row_cap != slot_level0) {
             BH_CUDA(slot_head.reserve(need, stream));
             BH_CUDA(cudaMemsetAsync(slot_head.p, 0xFF, slot_head.cap * sizeof(int32_t), stream));
-            slot_level0 = level0_rows;
+            slot_level0 = row_cap;
         }
         return 0;
     }
@@ -237,8 +367,10 @@ struct bh_index {
     void free_all() {
         nver0.release(); nverU.release();
         vecs.release(); nbr0.release(); upper_base_d.release(); upper_nbr.release(); slot_head.release();
-        sel_d.release(); conv_d.release(); build_counters.release();
-        counter.release(); q_d.release(); D_d.release(); I_d.release(); stats_d.release();
+        conv_d.release(); build_counters.release();
+        counter.release();
+        for (auto& c : pool) c->destroy();
+        pool.clear();
         items_d.release(); cand_lists.release(); cand_counts.release();
         e_slot.release(); e_src.release(); e_dst.release(); e_level.release(); e_next.release(); e_dist.release();
     }
@@ -246,28 +378,88 @@ struct bh_index {
 
 namespace {
 
-// storage->add: rows [n0, n0+n) into HBM, converting to fp16 on the device when that storage is on
+// Host rows [m][d] -> [m][dp] with a zero tail (d == dp: one straight copy).
+void copy_rows_padded(float* dst, const float* src, int64_t m, int d, int dp) {
+    if (d == dp) {
+        std::memcpy(dst, src, (size_t)m * d * sizeof(float));
+        return;
+    }
+    for (int64_t i = 0; i < m; i++) {
+        std::memcpy(dst + (size_t)i * dp, src + (size_t)i * d, (size_t)d * sizeof(float));
+        std::memset(dst + (size_t)i * dp + d, 0, (size_t)(dp - d) * sizeof(float));
+    }
+}
+
+// Same on the stream: `src` is host or device memory, `dst` device [m][dp] fp32.
+cudaError_t copy_rows_padded_async(float* dst, const float* src, int64_t m, int d, int dp,
+                                   cudaMemcpyKind kind, cudaStream_t stream) {
+    if (d == dp) return cudaMemcpyAsync(dst, src, (size_t)m * d * sizeof(float), kind, stream);
+    cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)m * dp * sizeof(float), stream);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy2DAsync(dst, (size_t)dp * sizeof(float), src, (size_t)d * sizeof(float),
+                             (size_t)d * sizeof(float), (size_t)m, kind, stream);
+}
+
+// storage->add: rows [n0, n0+n) into HBM (zero-padded to dp), converting to fp16 on the device when
+// that storage is on
 int upload_vectors(bh_index* h, int64_t n0, int64_t n, const float* x) {
-    const int d = h->d;
+    const int d = h->d, dp = h->dp;
     if (!h->half()) {
-        BH_CUDA(cudaMemcpyAsync(h->vecs.p + (size_t)n0 * d, x, (size_t)n * d * sizeof(float),
-                                cudaMemcpyHostToDevice, h->stream));
+        BH_CUDA(copy_rows_padded_async(h->vecs.p + (size_t)n0 * dp, x, n, d, dp, cudaMemcpyHostToDevice, h->stream));
         return 0;
     }
     const int64_t chunk = std::min<int64_t>(n, 1 << 20);
-    BH_CUDA(h->conv_d.reserve((size_t)chunk * d, h->stream));
+    BH_CUDA(h->conv_d.reserve((size_t)chunk * dp, h->stream));
     char* dst = reinterpret_cast<char*>(h->vecs.p);
     for (int64_t i0 = 0; i0 < n; i0 += chunk) {
         const int64_t m = std::min(chunk, n - i0);
-        BH_CUDA(cudaMemcpyAsync(h->conv_d.p, x + (size_t)i0 * d, (size_t)m * d * sizeof(float),
-                                cudaMemcpyHostToDevice, h->stream));
-        BH_CUDA(bh::launch_f32_to_f16(h->conv_d.p, dst + (size_t)(n0 + i0) * d * 2, (size_t)m * d, h->stream));
+        BH_CUDA(copy_rows_padded_async(h->conv_d.p, x + (size_t)i0 * d, m, d, dp, cudaMemcpyHostToDevice, h->stream));
+        BH_CUDA(bh::launch_f32_to_f16(h->conv_d.p, dst + (size_t)(n0 + i0) * dp * 2, (size_t)m * dp, h->stream));
     }
     return 0;
 }
 
-int search_device_impl(const bh_index* h, int64_t n, const float* xq_d, int64_t k, float* D_d,
-                       int64_t* I_d, int32_t* stats_d, const bh_search_params* params,
+// ---- search contexts -----------------------------------------------------------------------
+SearchCtx* acquire_ctx(const bh_index* h, bool primary_only) {
+    std::unique_lock<std::mutex> lk(h->pool_mu);
+    for (;;) {
+        const size_t lim = primary_only ? 1 : h->pool.size();
+        for (size_t i = 0; i < lim; i++)
+            if (!h->pool[i]->busy) {
+                h->pool[i]->busy = true;
+                return h->pool[i].get();
+            }
+        if (!primary_only && h->pool.size() < (size_t)kMaxSearchCtx) {
+            std::unique_ptr<SearchCtx> c(new SearchCtx());
+            const cudaError_t e = c->init(nullptr);
+            if (e != cudaSuccess) {
+                c->destroy();
+                fail(std::string("search: creating a search context failed: ") + cudaGetErrorString(e));
+                return nullptr;
+            }
+            c->busy = true;
+            h->pool.push_back(std::move(c));
+            return h->pool.back().get();
+        }
+        h->pool_cv.wait(lk);
+    }
+}
+struct CtxLease {  // gives the context back on every return path
+    const bh_index* h;
+    SearchCtx* c;
+    ~CtxLease() {
+        if (!c) return;
+        {
+            std::lock_guard<std::mutex> lk(h->pool_mu);
+            c->busy = false;
+        }
+        h->pool_cv.notify_all();
+    }
+};
+
+// One traversal launch: n queries at xq_d (device-addressable, 16-byte aligned rows of dp floats).
+int search_device_impl(const bh_index* h, cudaStream_t stream, int* counter, int64_t n, const float* xq_d,
+                       int64_t k, float* D_d, int64_t* I_d, int32_t* stats_d, const bh_search_params* params,
                        const uint8_t* sel_dev = nullptr) {
     const int efS = (params && params->efSearch > 0) ? params->efSearch : h->efSearch;
     bool crd = h->check_relative_distance;
@@ -276,14 +468,10 @@ int search_device_impl(const bh_index* h, int64_t n, const float* xq_d, int64_t 
     const int ef = (int)std::max<int64_t>(efS, k);
     if (ef > 4096) return fail("max(efSearch, k) > 4096 is not supported");
     const int rk = sel_dev ? (int)k : 0;  // selector-filtered result list lives beside the candidate list
-    const int hb = h->auto_hash_bits(ef + rk, params ? params->hash_bits : 0);
-    int W = h->auto_warps(ef + rk, hb, params ? params->warps_per_query : 0, n);
-    int G = W >= 4 ? 1 : 4 / W;
-    while (G * bh::beam_group_smem(h->d, ef, hb, h->deg0(), rk) > h->smem_optin && W < 4) {
-        W *= 2;
-        G = W >= 4 ? 1 : 4 / W;
-    }
-    if (G * bh::beam_group_smem(h->d, ef, hb, h->deg0(), rk) > h->smem_optin)
+    int vmode = 0, hb = 0;
+    h->pick_visited(ef + rk, params ? params->visited_policy : 0, params ? params->hash_bits : 0, vmode, hb);
+    int W = 1;
+    if (!h->pick_warps(ef, hb, rk, params ? params->warps_per_query : 0, n, W))
         return fail("efSearch/hash_bits need more shared memory than one SM has");
     bh::BeamTask t{};
     t.queries = xq_d;
@@ -296,11 +484,12 @@ int search_device_impl(const bh_index* h, int64_t n, const float* xq_d, int64_t 
     t.ef_stop = crd ? efS : INT_MAX;
     t.max_steps = crd ? INT_MAX : efS;
     t.hash_bits = hb;
+    t.visited_mode = vmode;
     t.stats = stats_d;
     t.sel = sel_dev;
-    t.counter = h->counter.p;
-    BH_CUDA(cudaMemsetAsync(h->counter.p, 0, sizeof(int), h->stream));
-    BH_CUDA(bh::launch_beam(h->view(), t, W, h->beam_variant(ef + rk, hb), h->num_sms, h->stream, nullptr));
+    t.counter = counter;
+    BH_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+    BH_CUDA(bh::launch_beam(h->view(), t, W, h->beam_variant(ef + rk, hb), h->num_sms, stream, nullptr));
     bh::count_launch();
     return 0;
 }
@@ -342,12 +531,13 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     if (h->ntotal + n > (int64_t)INT32_MAX - 1) return fail("add: more than 2^31-2 vectors per index");
     BH_CUDA(cudaSetDevice(h->device));
     const int64_t n0 = h->ntotal;
-    const int d = h->d, M = h->M, deg0 = h->deg0();
-    // Everything that can reject the call is checked BEFORE the level RNG advances or any state
-    // changes, so a failed add() leaves the index exactly as it was.
+    const int d = h->dp, M = h->M, deg0 = h->deg0();
+    // Argument errors are rejected BEFORE the level RNG advances or any state changes; later failures
+    // (allocation, launch configuration) are undone by `rollback` below.
     const int efc = h->efConstruction;
     if (efc < 1 || efc > 4096) return fail("efConstruction must be in [1, 4096]");
-    const int hb = h->auto_hash_bits(efc, h->bp.hash_bits);
+    int vmode = 0, hb = 0;
+    h->pick_visited(efc, h->bp.visited_policy, h->bp.hash_bits, vmode, hb);
     if (bh::beam_group_smem(d, efc, hb, deg0) > h->smem_optin)
         return fail("efConstruction/hash_bits need more shared memory than one SM has");
     if (preset_levels)
@@ -371,6 +561,30 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
                 std::chrono::duration<double, std::milli>(now - t_prev).count());
         t_prev = now;
     };
+
+    // From here on host state changes (level RNG, levels, ntotal, entry point). Any failure before the
+    // rounds have been enqueued and completed puts all of it back, so a failed add() — allocation
+    // failure included — leaves the index answering searches exactly as before. (Device rows beyond
+    // the old ntotal may have been written; nothing reads them.) A kernel fault inside the rounds is
+    // a sticky CUDA error and takes the context down whatever the host state says.
+    struct Rollback {
+        bh_index* h;
+        std::mt19937 rng;
+        size_t nlev;
+        int64_t n_upper_rows, ntotal;
+        int entry_point, max_level;
+        bool armed = true;
+        ~Rollback() {
+            if (!armed) return;
+            h->rng = rng;
+            h->levels.resize(nlev);
+            h->upper_base.resize(nlev);
+            h->n_upper_rows = n_upper_rows;
+            h->ntotal = ntotal;
+            h->entry_point = entry_point;
+            h->max_level = max_level;
+        }
+    } rollback{h, h->rng, h->levels.size(), h->n_upper_rows, h->ntotal, h->entry_point, h->max_level};
 
     // -- prepare_level_tab (App. A.2): levels, row allocation
     std::vector<int32_t> new_levels(n);
@@ -479,7 +693,10 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
             rounds.push_back(r);
         }
     }
-    if (items.empty()) return 0;
+    if (items.empty()) {
+        rollback.armed = false;
+        return 0;
+    }
     lap("order + round schedule");
     size_t max_items = 0;
     for (const Round& r : rounds) max_items = std::max(max_items, (size_t)(r.item_end - r.item_begin));
@@ -518,11 +735,14 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
             t.ef_stop = INT_MAX;
             t.max_steps = INT_MAX;
             t.hash_bits = hb;
+            t.visited_mode = vmode;
             t.stats = nullptr;
             t.build_counters = h->build_counters.p;
             t.counter = h->counter.p;
             BH_CUDA(cudaMemsetAsync(h->counter.p, 0, sizeof(int), h->stream));
-            const int W = h->auto_warps(efc, hb, h->bp.warps_per_query, n_items);
+            int W = 1;
+            if (!h->pick_warps(efc, hb, 0, h->bp.warps_per_query, n_items, W))
+                return fail("efConstruction/hash_bits need more shared memory than one SM has");
             BH_CUDA(bh::launch_beam(g, t, W, h->beam_variant(efc, hb), h->num_sms, h->stream, nullptr));
             bh::BuildBatch b{};
             b.items = t.items;
@@ -558,6 +778,7 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
     BH_CUDA(cudaEventElapsedTime(&h->last_build_ms, h->ev0, h->ev1));
     BH_CUDA(cudaMemcpy(h->last_build_counters, h->build_counters.p, 6 * sizeof(unsigned long long),
                        cudaMemcpyDeviceToHost));
+    rollback.armed = false;
     return 0;
 }
 
@@ -573,7 +794,7 @@ int64_t bh_launch_count(void) { return (int64_t)bh::g_launches.load(); }
 int bh_index_create(bh_index** out, int d, int M, int metric, int device) {
     if (!out) return fail("create: out is null");
     *out = nullptr;
-    if (d <= 0 || d % 4 != 0 || d > 2048) return fail("create: d must be a multiple of 4 in [4, 2048]");
+    if (d <= 0 || d > 2048) return fail("create: d must be in [1, 2048]");
     if (M < 2 || 2 * M > bh::kMaxDeg) return fail("create: M must be in [2, 64]");
     if (metric != BH_METRIC_L2 && metric != BH_METRIC_INNER_PRODUCT)
         return fail("create: metric must be METRIC_L2 (1) or METRIC_INNER_PRODUCT (0)");
@@ -589,6 +810,7 @@ int bh_index_create(bh_index** out, int d, int M, int metric, int device) {
     if (prop.major < 10) return fail("create: this library is built for sm_100a (B200) only");
     bh_index* h = new bh_index();
     h->d = d;
+    h->set_padded_dim();
     h->M = M;
     h->metric = metric;
     h->device = device;
@@ -600,6 +822,15 @@ int bh_index_create(bh_index** out, int d, int M, int metric, int device) {
         h->counter.reserve(4, h->stream) != cudaSuccess) {
         delete h;
         return fail("create: stream/event/alloc failed");
+    }
+    {  // primary search context: its lane 0 is the index's stream
+        std::unique_ptr<SearchCtx> c(new SearchCtx());
+        if (c->init(h->stream) != cudaSuccess) {
+            c->destroy();
+            bh_index_free(h);
+            return fail("create: search context allocation failed");
+        }
+        h->pool.push_back(std::move(c));
     }
     *out = h;
     return 0;
@@ -632,16 +863,15 @@ static int reset_locked(bh_index* h) {
 
 int bh_index_reset(bh_index* h) {
     if (!h) return fail("null index");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::unique_lock<std::shared_mutex> lk(h->rw);
     return reset_locked(h);
 }
 
 int bh_index_set_vector_storage(bh_index* h, int storage) {
     if (!h) return fail("null index");
     if (storage != BH_STORAGE_F32 && storage != BH_STORAGE_F16) return fail("unknown storage kind");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::unique_lock<std::shared_mutex> lk(h->rw);
     if (h->ntotal != 0) return fail("set_vector_storage: the index is not empty");
-    if (storage == BH_STORAGE_F16 && h->d % 8 != 0) return fail("fp16 storage needs d % 8 == 0");
     if (storage != h->storage) {  // capacities are counted in rows of the old width: start over
         cudaSetDevice(h->device);
         cudaStreamSynchronize(h->stream);
@@ -650,8 +880,10 @@ int bh_index_set_vector_storage(bh_index* h, int storage) {
         h->upper_base_d.release();
         h->nver0.release();
         h->slot_level0 = 0;
+        h->row_cap = 0;
     }
     h->storage = storage;
+    h->set_padded_dim();
     return 0;
 }
 int bh_index_get_vector_storage(const bh_index* h) { return h ? h->storage : -1; }
@@ -663,13 +895,13 @@ int bh_index_train(bh_index* h, int64_t, const float*) {
 
 int bh_index_add(bh_index* h, int64_t n, const float* x) {
     if (!h) return fail("null index");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::unique_lock<std::shared_mutex> lk(h->rw);
     return add_impl(h, n, x, nullptr, nullptr);
 }
 
 int bh_index_add_ex(bh_index* h, int64_t n, const float* x, const int32_t* levels, const int32_t* order) {
     if (!h) return fail("null index");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::unique_lock<std::shared_mutex> lk(h->rw);
     return add_impl(h, n, x, levels, order);
 }
 
@@ -678,14 +910,28 @@ int bh_index_search_device(const bh_index* h, int64_t n, const float* x, int64_t
     if (!h) return fail("null index");
     if (n < 0 || k <= 0) return fail("search: need n >= 0 and k > 0");
     if (n == 0) return 0;
-    if (h->ntotal == 0) return fail("search_device: empty index");
+    if (!x || !distances || !labels) return fail("search_device: null buffer");
     if (n > INT32_MAX) return fail("search_device: n too large for one call");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::shared_lock<std::shared_mutex> lk(h->rw);
+    if (h->ntotal == 0) return fail("search_device: empty index");
     BH_CUDA(cudaSetDevice(h->device));
     if (params && params->sel_bitmap && params->sel_bitmap_bytes < (h->ntotal + 7) / 8)
         return fail("search: sel_bitmap is smaller than (ntotal + 7) / 8 bytes");
-    return search_device_impl(h, n, x, k, distances, labels, params ? params->stats : nullptr, params,
-                              params ? params->sel_bitmap : nullptr);
+    // always the primary context: its lane 0 is the index's own stream (bh_index_stream)
+    CtxLease lease{h, acquire_ctx(h, true)};
+    if (!lease.c) return 1;
+    SearchCtx& c = *lease.c;
+    cudaStream_t st = c.lane[0].stream;
+    // Each query row is fetched with one bulk (TMA) copy, which needs a 16-byte aligned source. Rows of a
+    // d % 4 != 0 index, or a buffer at an odd offset (a tensor view), are first re-laid into an aligned,
+    // zero-padded staging buffer on the stream — never handed to the kernel as they are.
+    if (h->d != h->dp || (reinterpret_cast<uintptr_t>(x) & 15) != 0) {
+        BH_CUDA(c.q_d.reserve((size_t)n * h->dp, st));
+        BH_CUDA(copy_rows_padded_async(c.q_d.p, x, n, h->d, h->dp, cudaMemcpyDeviceToDevice, st));
+        x = c.q_d.p;
+    }
+    return search_device_impl(h, st, c.counters.p, n, x, k, distances, labels, params ? params->stats : nullptr,
+                              params, params ? params->sel_bitmap : nullptr);
 }
 
 int bh_index_search(const bh_index* h, int64_t n, const float* x, int64_t k, float* distances,
@@ -694,7 +940,7 @@ int bh_index_search(const bh_index* h, int64_t n, const float* x, int64_t k, flo
     if (n < 0 || k <= 0) return fail("search: need n >= 0 and k > 0");
     if (n == 0) return 0;
     if (!x || !distances || !labels) return fail("search: null buffer");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::shared_lock<std::shared_mutex> lk(h->rw);
     if (h->ntotal == 0) {  // HNSW::search returns at once on an empty graph: heaps stay (FLT_MAX,-1)
         const float pad = h->metric == BH_METRIC_L2 ? FLT_MAX : -FLT_MAX;
         for (int64_t i = 0; i < n * k; i++) {
@@ -704,19 +950,26 @@ int bh_index_search(const bh_index* h, int64_t n, const float* x, int64_t k, flo
         return 0;
     }
     BH_CUDA(cudaSetDevice(h->device));
+    CtxLease lease{h, acquire_ctx(h, false)};
+    if (!lease.c) return 1;
+    SearchCtx& c = *lease.c;
+    SearchLane& l0 = c.lane[0];
     const uint8_t* sel_dev = nullptr;
     if (params && params->sel_bitmap) {
         const int64_t need = (h->ntotal + 7) / 8;
         if (params->sel_bitmap_bytes < need) return fail("search: sel_bitmap is smaller than (ntotal + 7) / 8 bytes");
-        BH_CUDA(h->sel_d.reserve((size_t)need, h->stream));
-        BH_CUDA(cudaMemcpyAsync(h->sel_d.p, params->sel_bitmap, (size_t)need, cudaMemcpyHostToDevice, h->stream));
-        sel_dev = h->sel_d.p;
+        BH_CUDA(c.sel_d.reserve((size_t)need, l0.stream));
+        BH_CUDA(cudaMemcpyAsync(c.sel_d.p, params->sel_bitmap, (size_t)need, cudaMemcpyHostToDevice, l0.stream));
+        BH_CUDA(cudaStreamSynchronize(l0.stream));  // the other lanes read it too
+        sel_dev = c.sel_d.p;
     }
-    // Zero-copy path: when the caller's buffers are page-locked (cudaHostAlloc / cudaHostRegister,
-    // e.g. torch pinned tensors) they are device-addressable under UVA, so the kernel reads each
-    // query straight from host memory with its TMA bulk copy and writes the k results back over
-    // PCIe — the transfers overlap the traversal instead of bracketing it.
-    if (n <= INT32_MAX && !(params && params->stats)) {
+    int32_t* stats_host = params ? params->stats : nullptr;
+
+    // (1) Zero-copy path: the caller's buffers are page-locked (cudaHostAlloc / cudaHostRegister, e.g.
+    // torch pinned tensors) and the rows are TMA-aligned, so they are device-addressable under UVA: the
+    // kernel reads each query straight from host memory with its bulk copy and writes the k results back
+    // over PCIe — the transfers overlap the traversal instead of bracketing it.
+    if (!stats_host && h->d == h->dp && n <= INT32_MAX) {
         auto dev_ptr = [](const void* p) -> void* {
             cudaPointerAttributes at;
             if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
@@ -728,46 +981,77 @@ int bh_index_search(const bh_index* h, int64_t n, const float* x, int64_t k, flo
         void* xd = dev_ptr(x);
         void* dd = dev_ptr(distances);
         void* ld = dev_ptr(labels);
-        if (xd && dd && ld) {
-            BH_CUDA(cudaEventRecord(h->ev0, h->stream));
-            if (int rc = search_device_impl(h, n, (const float*)xd, k, (float*)dd, (int64_t*)ld, nullptr, params, sel_dev))
+        if (xd && dd && ld && (reinterpret_cast<uintptr_t>(xd) & 15) == 0) {
+            BH_CUDA(cudaEventRecord(c.ev0, l0.stream));
+            if (int rc = search_device_impl(h, l0.stream, c.counters.p, n, (const float*)xd, k, (float*)dd,
+                                            (int64_t*)ld, nullptr, params, sel_dev))
                 return rc;
-            BH_CUDA(cudaEventRecord(h->ev1, h->stream));
-            BH_CUDA(cudaStreamSynchronize(h->stream));
-            BH_CUDA(cudaEventElapsedTime(&h->last_search_ms, h->ev0, h->ev1));
+            BH_CUDA(cudaEventRecord(c.ev1, l0.stream));
+            BH_CUDA(cudaStreamSynchronize(l0.stream));
+            float ms = 0.f;
+            BH_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+            h->last_search_ms = ms;
             return 0;
         }
     }
-    const int64_t chunk = 1 << 18;
-    const int64_t nb = std::min(n, chunk);
-    BH_CUDA(h->q_d.reserve((size_t)nb * h->d, h->stream));
-    BH_CUDA(h->D_d.reserve((size_t)nb * k, h->stream));
-    BH_CUDA(h->I_d.reserve((size_t)nb * k, h->stream));
-    int32_t* stats_host = params ? params->stats : nullptr;
-    if (stats_host) BH_CUDA(h->stats_d.reserve((size_t)nb * 4, h->stream));
-    float total_ms = 0.f;
-    for (int64_t i0 = 0; i0 < n; i0 += chunk) {
-        const int64_t m = std::min(chunk, n - i0);
-        BH_CUDA(cudaMemcpyAsync(h->q_d.p, x + (size_t)i0 * h->d, (size_t)m * h->d * sizeof(float),
-                                cudaMemcpyHostToDevice, h->stream));
-        BH_CUDA(cudaEventRecord(h->ev0, h->stream));
-        if (int rc = search_device_impl(h, m, h->q_d.p, k, h->D_d.p, h->I_d.p,
-                                        stats_host ? h->stats_d.p : nullptr, params, sel_dev))
-            return rc;
-        BH_CUDA(cudaEventRecord(h->ev1, h->stream));
-        BH_CUDA(cudaMemcpyAsync(distances + (size_t)i0 * k, h->D_d.p, (size_t)m * k * sizeof(float),
-                                cudaMemcpyDeviceToHost, h->stream));
-        BH_CUDA(cudaMemcpyAsync(labels + (size_t)i0 * k, h->I_d.p, (size_t)m * k * sizeof(int64_t),
-                                cudaMemcpyDeviceToHost, h->stream));
+
+    // (2) Pageable callers (a faiss drop-in passes plain numpy / malloc memory): the batch is cut into
+    // chunks that go round-robin over the context's lanes. Per chunk the CPU copies (and zero-pads) the
+    // queries into the lane's page-locked staging, the lane's kernel reads them from there and writes
+    // D / I (/ stats) into page-locked result staging, and the CPU copies those out when the lane is
+    // next needed or at the end. Staging chunk i+1 overlaps the traversal of chunk i, and the chunks'
+    // kernels fill each other's tails; there is no separate H2D / D2H phase.
+    const int d = h->d, dp = h->dp;
+    int64_t chunk = (n + 3) / 4;                       // 4 chunks for a mid-size batch
+    chunk = std::max<int64_t>(chunk, 2048);            // small batches: one launch
+    chunk = std::min<int64_t>(chunk, 32768);           // bounds the staging memory
+    chunk = std::min<int64_t>(chunk, n);
+    auto drain = [&](SearchLane& l) -> int {
+        if (l.pending_i0 < 0) return 0;
+        BH_CUDA(cudaEventSynchronize(l.done));
+        std::memcpy(distances + (size_t)l.pending_i0 * k, l.hD.p, (size_t)l.pending_m * k * sizeof(float));
+        std::memcpy(labels + (size_t)l.pending_i0 * k, l.hI.p, (size_t)l.pending_m * k * sizeof(int64_t));
         if (stats_host)
-            BH_CUDA(cudaMemcpyAsync(stats_host + (size_t)i0 * 4, h->stats_d.p, (size_t)m * 4 * sizeof(int32_t),
-                                    cudaMemcpyDeviceToHost, h->stream));
-        BH_CUDA(cudaStreamSynchronize(h->stream));
-        float ms = 0.f;
-        BH_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-        total_ms += ms;
+            std::memcpy(stats_host + (size_t)l.pending_i0 * 4, l.hS.p, (size_t)l.pending_m * 4 * sizeof(int32_t));
+        l.pending_i0 = -1;
+        return 0;
+    };
+    struct PendingGuard {  // an error return must not leave a chunk marked pending for the next call
+        SearchCtx& c;
+        ~PendingGuard() {
+            for (int i = 0; i < kLanes; i++) {
+                if (c.lane[i].pending_i0 >= 0) cudaStreamSynchronize(c.lane[i].stream);
+                c.lane[i].pending_i0 = -1;
+            }
+        }
+    } guard{c};
+    BH_CUDA(cudaEventRecord(c.ev0, l0.stream));
+    int li = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += chunk, li = (li + 1) % kLanes) {
+        const int64_t m = std::min(chunk, n - i0);
+        SearchLane& l = c.lane[li];
+        if (int rc = drain(l)) return rc;
+        BH_CUDA(l.hq.reserve((size_t)chunk * dp));
+        BH_CUDA(l.hD.reserve((size_t)chunk * k));
+        BH_CUDA(l.hI.reserve((size_t)chunk * k));
+        if (stats_host) BH_CUDA(l.hS.reserve((size_t)chunk * 4));
+        copy_rows_padded(l.hq.p, x + (size_t)i0 * d, m, d, dp);
+        if (int rc = search_device_impl(h, l.stream, c.counters.p + li, m, l.hq.dev, k, l.hD.dev, l.hI.dev,
+                                        stats_host ? l.hS.dev : nullptr, params, sel_dev))
+            return rc;
+        BH_CUDA(cudaEventRecord(l.done, l.stream));
+        l.pending_i0 = i0;
+        l.pending_m = m;
     }
-    h->last_search_ms = total_ms;
+    for (int i = 1; i < kLanes; i++)  // device-side span of the call: lane 0 waits for the others
+        if (c.lane[i].pending_i0 >= 0) BH_CUDA(cudaStreamWaitEvent(l0.stream, c.lane[i].done, 0));
+    BH_CUDA(cudaEventRecord(c.ev1, l0.stream));
+    for (int i = 0; i < kLanes; i++)
+        if (int rc = drain(c.lane[(li + i) % kLanes])) return rc;  // oldest chunk first
+    BH_CUDA(cudaEventSynchronize(c.ev1));
+    float ms = 0.f;
+    BH_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+    h->last_search_ms = ms;
     return 0;
 }
 
@@ -779,26 +1063,28 @@ int bh_index_reconstruct(const bh_index* h, int64_t key, float* out) {
 
 int bh_index_reconstruct_n(const bh_index* h, int64_t i0, int64_t ni, float* out) {
     if (!h) return fail("null index");
+    if (!out) return fail("reconstruct_n: null buffer");
+    std::shared_lock<std::shared_mutex> lk(h->rw);
     if (i0 < 0 || ni < 0 || i0 + ni > h->ntotal) return fail("reconstruct_n: range out of bounds");
     if (ni == 0) return 0;
-    std::lock_guard<std::mutex> lk(h->mu);
     BH_CUDA(cudaSetDevice(h->device));
+    // own stream-less copies (cudaMemcpy*): reconstruct may run beside searches on the index's stream
+    const int d = h->d, dp = h->dp;
     if (!h->half()) {
-        BH_CUDA(cudaMemcpyAsync(out, h->vecs.p + (size_t)i0 * h->d, (size_t)ni * h->d * sizeof(float),
-                                cudaMemcpyDeviceToHost, h->stream));
+        BH_CUDA(cudaMemcpy2D(out, (size_t)d * sizeof(float), h->vecs.p + (size_t)i0 * dp, (size_t)dp * sizeof(float),
+                             (size_t)d * sizeof(float), (size_t)ni, cudaMemcpyDeviceToHost));
     } else {  // widen on the device (exact), then copy: the caller always sees fp32
+        std::lock_guard<std::mutex> cl(h->conv_mu);
         const int64_t chunk = std::min<int64_t>(ni, 1 << 20);
-        BH_CUDA(h->conv_d.reserve((size_t)chunk * h->d, h->stream));
+        BH_CUDA(h->conv_d.reserve((size_t)chunk * dp, nullptr));
         const char* src = reinterpret_cast<const char*>(h->vecs.p);
         for (int64_t j0 = 0; j0 < ni; j0 += chunk) {
             const int64_t m = std::min(chunk, ni - j0);
-            BH_CUDA(bh::launch_f16_to_f32(src + (size_t)(i0 + j0) * h->d * 2, h->conv_d.p, (size_t)m * h->d, h->stream));
-            BH_CUDA(cudaMemcpyAsync(out + (size_t)j0 * h->d, h->conv_d.p, (size_t)m * h->d * sizeof(float),
-                                    cudaMemcpyDeviceToHost, h->stream));
-            BH_CUDA(cudaStreamSynchronize(h->stream));
+            BH_CUDA(bh::launch_f16_to_f32(src + (size_t)(i0 + j0) * dp * 2, h->conv_d.p, (size_t)m * dp, nullptr));
+            BH_CUDA(cudaMemcpy2D(out + (size_t)j0 * d, (size_t)d * sizeof(float), h->conv_d.p, (size_t)dp * sizeof(float),
+                                 (size_t)d * sizeof(float), (size_t)m, cudaMemcpyDeviceToHost));
         }
     }
-    BH_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -842,6 +1128,7 @@ int64_t bh_index_neighbors_size(const bh_index* h) {
 
 int bh_index_export_graph(const bh_index* h, int32_t* levels, uint64_t* offsets, int32_t* neighbors) {
     if (!h) return fail("null index");
+    std::shared_lock<std::shared_mutex> lk(h->rw);
     BH_CUDA(cudaSetDevice(h->device));
     const int64_t n = h->ntotal;
     const int deg0 = h->deg0(), M = h->M;
@@ -872,7 +1159,7 @@ int bh_index_import_graph(bh_index* h, int64_t n, const float* x, const int32_t*
     if (n <= 0 || !x || !levels || !neighbors) return fail("import: bad arguments");
     if (n > (int64_t)INT32_MAX - 1) return fail("import: too many vectors");
     if (entry_point < 0 || entry_point >= n) return fail("import: entry point out of range");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::unique_lock<std::shared_mutex> lk(h->rw);
     BH_CUDA(cudaSetDevice(h->device));
     const int M = h->M, deg0 = h->deg0();
     std::vector<int32_t> ub(n);
@@ -931,7 +1218,7 @@ int bh_index_last_build_counters(const bh_index* h, uint64_t out[6]) {
     for (int i = 0; i < 6; i++) out[i] = h->last_build_counters[i];
     return 0;
 }
-float bh_index_last_search_ms(const bh_index* h) { return h ? h->last_search_ms : -1.f; }
+float bh_index_last_search_ms(const bh_index* h) { return h ? h->last_search_ms.load() : -1.f; }
 
 int bh_merge_topk_device(int nshard, int64_t nq, int64_t k, int metric, const float* D_all,
                          const int64_t* I_all, const int64_t* id_offsets, float* D_out, int64_t* I_out,

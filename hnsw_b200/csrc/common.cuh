@@ -11,6 +11,11 @@ constexpr unsigned long long kExpanded = 0x80000000ull;  // "already expanded" b
 constexpr int kMaxDeg = 128;                       // 2*M <= 128
 constexpr int kMaxIdsPerLane = kMaxDeg / 32;
 
+// Visited-set policies (BeamTask::visited_mode). The table is `4 << hash_bits` bytes in every mode.
+constexpr int kVisitedExact = 0;    // open addressing, 32-bit slots, exact until 3/4 full, then clear + re-seed
+constexpr int kVisitedAssoc16 = 1;  // 8-way buckets of 16-bit quotients, FIFO eviction (ntotal <= 2^(hash_bits+14))
+constexpr int kVisitedAssoc32 = 2;  // 4-way buckets of 32-bit ids, FIFO eviction
+
 // Device-side view of one index shard (SURVEY §8a1/a2 re-laid-out for HBM):
 //   vecs       [ntotal][d] row-major (faiss IndexFlat codes): fp32, or IEEE fp16 when `half` is set
 //              (opt-in storage mode). Either way a row is `nchunk` 16-byte chunks, so row addressing
@@ -132,6 +137,12 @@ __device__ __forceinline__ uint4 lds128_volatile(const void* smem_ptr) {
                  : "r"(smem_u32(smem_ptr))
                  : "memory");
     return v;
+}
+
+__device__ __forceinline__ void sts128_volatile(void* smem_ptr, const uint4& v) {
+    asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(smem_ptr)), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
 }
 
 // 128-bit read-only gather load that does not allocate in L1 (rows are not reused by the SM).

@@ -24,7 +24,8 @@ struct BeamTask {
     int ef;         // list capacity
     int ef_stop;    // count_below threshold (INT_MAX = off)
     int max_steps;  // nstep limit (INT_MAX = off)
-    int hash_bits;
+    int hash_bits;     // visited table = 4 << hash_bits bytes per query
+    int visited_mode;  // kVisitedExact / kVisitedAssoc16 / kVisitedAssoc32 (beam.cuh)
     int32_t* stats;  // device int32[n_items][4] or null
     unsigned long long* build_counters;  // device [6] or null: {ndis0, nhops0, ndis_up, nhops_up, sel_rows, bl_rows}
     const uint8_t* sel;  // device IDSelectorBitmap over the shard's ids, or null (search mode only)

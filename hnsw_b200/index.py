@@ -123,7 +123,7 @@ class IndexHNSWFlat:
 
     def search(self, x, k: int, params: SearchParams | None = None, efSearch: int | None = None,
                stats: bool = False, out=None, warps_per_query: int = 0, hash_bits: int = 0,
-               sel_bitmap=None):
+               sel_bitmap=None, visited_policy: int = 0):
         """faiss Index.search → (D, I). `out=(D, I)` reuses caller buffers (e.g. pinned).
         `sel_bitmap`: uint8 array in faiss IDSelectorBitmap layout (np.packbits(mask, bitorder="little"));
         only ids whose bit is set can be returned (SearchParametersHNSW.sel semantics)."""
@@ -134,9 +134,13 @@ class IndexHNSWFlat:
             I = np.empty((nq, k), np.int64)
         else:
             D, I = out
+            for a, dt in ((D, np.float32), (I, np.int64)):  # raw pointers go to C: refuse anything else
+                if not (isinstance(a, np.ndarray) and a.dtype == dt and a.shape == (nq, k) and a.flags.c_contiguous):
+                    raise ValueError(f"out= needs C-contiguous ({nq}, {k}) float32 / int64 arrays")
         st = np.zeros((nq, 4), np.int32) if stats else None
         if params is None:
-            params = SearchParams(int(efSearch or 0), 0, int(warps_per_query), int(hash_bits), None, None, 0)
+            params = SearchParams(int(efSearch or 0), 0, int(warps_per_query), int(hash_bits), None, None, 0,
+                                  int(visited_policy), 0)
         if st is not None:
             params.stats = st.ctypes.data
         if sel_bitmap is not None:
@@ -149,9 +153,10 @@ class IndexHNSWFlat:
 
     def search_device(self, xq_ptr: int, nq: int, k: int, D_ptr: int, I_ptr: int,
                       efSearch: int = 0, stats_ptr: int = 0, warps_per_query: int = 0,
-                      hash_bits: int = 0):
+                      hash_bits: int = 0, visited_policy: int = 0):
         """Enqueue a search on device buffers (raw pointers); no host sync."""
-        p = SearchParams(int(efSearch), 0, int(warps_per_query), int(hash_bits), stats_ptr or None, None, 0)
+        p = SearchParams(int(efSearch), 0, int(warps_per_query), int(hash_bits), stats_ptr or None, None, 0,
+                         int(visited_policy), 0)
         _lib.check(_lib.lib().bh_index_search_device(self._h, int(nq), xq_ptr, int(k), D_ptr, I_ptr,
                                                      C.byref(p)))
 
@@ -171,8 +176,9 @@ class IndexHNSWFlat:
         return out
 
     # ---- engine extras
-    def set_build_params(self, max_batch=0, batch_divisor=0, warps_per_query=0, hash_bits=0):
-        p = BuildParams(int(max_batch), int(batch_divisor), int(warps_per_query), int(hash_bits))
+    def set_build_params(self, max_batch=0, batch_divisor=0, warps_per_query=0, hash_bits=0, visited_policy=0):
+        p = BuildParams(int(max_batch), int(batch_divisor), int(warps_per_query), int(hash_bits),
+                        int(visited_policy))
         _lib.check(_lib.lib().bh_index_set_build_params(self._h, C.byref(p)))
 
     @property

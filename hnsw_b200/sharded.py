@@ -68,14 +68,20 @@ class ShardedIndexHNSWFlat:
         if self._on_gpu():
             from .index import merge_topk_device
             q = torch.as_tensor(np.ascontiguousarray(xq, np.float32)).to(self.device) \
-                if not isinstance(xq, torch.Tensor) else xq.to(self.device).contiguous()
+                if not isinstance(xq, torch.Tensor) else xq.to(self.device, torch.float32).contiguous()
             dist.broadcast(q, src=src, group=self.group)
             Dl = torch.empty(nq, k, device=self.device)
             Il = torch.empty(nq, k, dtype=torch.int64, device=self.device)
             cur = torch.cuda.current_stream(self.device)
             ist = torch.cuda.ExternalStream(self.local.stream_ptr, device=self.device)
             ist.wait_stream(cur)
-            self.local.search_device(q.data_ptr(), nq, k, Dl.data_ptr(), Il.data_ptr(), efSearch=efSearch or 0)
+            if self.local.ntotal == 0:
+                # an empty shard contributes empty lists (faiss pads with +/-FLT_MAX, -1); raising here
+                # would leave the peers blocked in the collective below
+                Dl.fill_(3.4028234663852886e38 if self.metric_type == 1 else -3.4028234663852886e38)
+                Il.fill_(-1)
+            else:
+                self.local.search_device(q.data_ptr(), nq, k, Dl.data_ptr(), Il.data_ptr(), efSearch=efSearch or 0)
             cur.wait_stream(ist)
             Dg = torch.empty(self.world, nq, k, device=self.device)
             Ig = torch.empty(self.world, nq, k, dtype=torch.int64, device=self.device)

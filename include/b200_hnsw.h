@@ -34,7 +34,8 @@ typedef struct bh_search_params {
     int32_t efSearch;                /* <=0: use the index's hnsw.efSearch */
     int32_t check_relative_distance; /* 0: index default, 1: on, 2: off */
     int32_t warps_per_query;         /* 0: auto; 1,2,4,8: warps cooperating on one query */
-    int32_t hash_bits;               /* 0: auto; log2 of the visited-hash slots per query */
+    int32_t hash_bits;               /* 0: auto; else the visited table is 4 << hash_bits bytes per query
+                                        (with visited_policy 0 a non-zero value selects the exact table) */
     int32_t* stats;                  /* optional int32[n][4]: {ndis L0, nhops L0, ndis upper,
                                         nhops upper}; host ptr (device ptr for *_device) */
     const uint8_t* sel_bitmap;       /* optional faiss::IDSelectorBitmap (SearchParametersHNSW::sel):
@@ -42,6 +43,13 @@ typedef struct bh_search_params {
                                         As in faiss it filters results only, not the traversal.
                                         host ptr (device ptr for *_device); NULL = no selector */
     int64_t sel_bitmap_bytes;        /* size of sel_bitmap, must be >= (ntotal + 7) / 8 */
+    int32_t visited_policy;          /* visited-set policy (faiss VisitedTable). Results never depend on it,
+                                        only the number of distance evaluations does:
+                                        0 auto: hash_bits == 0 -> set-associative forgetful table (default);
+                                                hash_bits  > 0 -> exact table of 2^hash_bits slots
+                                        1 exact until 3/4 full, then cleared and re-seeded from the list
+                                        2 set-associative, FIFO eviction per 16-byte bucket */
+    int32_t reserved_;               /* keep zero */
 } bh_search_params;
 
 /* Build-time knobs (no faiss equivalent: faiss's concurrency is the OpenMP thread count). */
@@ -51,6 +59,7 @@ typedef struct bh_build_params {
                                 (>=1 point); <=0: auto. max_batch=1 => faiss's sequential order */
     int32_t warps_per_query; /* 0: auto */
     int32_t hash_bits;       /* 0: auto */
+    int32_t visited_policy;  /* as bh_search_params.visited_policy */
 } bh_build_params;
 
 /* vector storage inside the index (the API is fp32 either way) */

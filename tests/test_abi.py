@@ -37,8 +37,8 @@ def test_version_and_error_channel():
     L = _lib.lib()
     assert b"sm_100a" in L.bh_version()
     h = C.c_void_p()
-    assert L.bh_index_create(C.byref(h), 7, 32, 1, 0) != 0          # d not a multiple of 4
-    assert "multiple of 4" in _lib.last_error()
+    assert L.bh_index_create(C.byref(h), 4096, 32, 1, 0) != 0       # d out of range
+    assert "[1, 2048]" in _lib.last_error()
     assert L.bh_index_create(C.byref(h), 128, 100, 1, 0) != 0       # M too large
     assert L.bh_index_create(C.byref(h), 128, 32, 5, 0) != 0        # unknown metric
     assert L.bh_index_ntotal(None) == -1

@@ -10,7 +10,28 @@ import pytest
 from hnsw_b200.datasets import synthetic_dataset
 
 
-def model_search(xb, g, cum, q, k, ef_search, check_rel=True, visited_cap=None, sel=None, dist=None):
+class AssocVisited:
+    """The default visited policy of the kernel (beam.cuh assoc_test_and_set): `buckets` FIFO buckets of
+    `ways` entries addressed by a multiplicative hash; nothing is ever cleared, old entries fall out."""
+
+    def __init__(self, buckets, ways):
+        self.t = [[] for _ in range(buckets)]
+        self.bits = int(np.log2(buckets))
+        self.ways = ways
+
+    def test_and_set(self, v):
+        b = ((v * 2654435761) & 0xFFFFFFFF) >> (32 - self.bits) if self.bits else 0
+        t = self.t[b]
+        if v in t:
+            return False
+        if len(t) == self.ways:
+            t.pop(0)
+        t.append(v)
+        return True
+
+
+def model_search(xb, g, cum, q, k, ef_search, check_rel=True, visited_cap=None, sel=None, dist=None,
+                 assoc=None):
     levels, offsets, nb = g["levels"], g["offsets"].astype(np.int64), g["neighbors"]
     row = lambda v, l: nb[offsets[v] + cum[l]: offsets[v] + cum[l + 1]]
     # greedy descent (argmin with first-index ties == sequential strict-< scan)
@@ -32,6 +53,8 @@ def model_search(xb, g, cum, q, k, ef_search, check_rel=True, visited_cap=None, 
     lst = [(dcur, cur, False)]          # (dist, id, expanded), kept sorted by (dist, id)
     res = [(dcur, cur)] if (sel is None or sel[cur]) else []
     visited = {cur}
+    if assoc is not None:
+        assoc.test_and_set(cur)
     ndis = nhops = nstep = 0
     while True:
         pos = next((i for i, e in enumerate(lst) if not e[2]), -1)
@@ -45,7 +68,10 @@ def model_search(xb, g, cum, q, k, ef_search, check_rel=True, visited_cap=None, 
             visited = {e[1] for e in lst} | {e[1] for e in res}
         new = []
         for v in r:
-            if int(v) not in visited:
+            if assoc is not None:
+                if assoc.test_and_set(int(v)):
+                    new.append(int(v))
+            elif int(v) not in visited:
                 visited.add(int(v))
                 new.append(int(v))
         nhops += 1
@@ -53,11 +79,13 @@ def model_search(xb, g, cum, q, k, ef_search, check_rel=True, visited_cap=None, 
         ndis += len(new)
         scored = [(np.float32(dist(q, xb[v])), v) for v in new]
         thr = (lst[-1][0], lst[-1][1]) if len(lst) == ef else (np.inf, 1 << 62)
-        acc = [(d, v, False) for d, v in scored if (d, v) < thr]
+        # a re-scored vertex that is still listed arrives with the identical key: the merge drops it
+        listed = {(e[0], e[1]) for e in lst}
+        acc = [(d, v, False) for d, v in scored if (d, v) < thr and (d, v) not in listed]
         lst = sorted(lst + acc, key=lambda e: (e[0], e[1]))[:ef]
         if sel is not None:
             rthr = res[-1] if len(res) == k else (np.inf, 1 << 62)
-            res = sorted(res + [(d, v) for d, v in scored if sel[v] and (d, v) < rthr])[:k]
+            res = sorted(res + [(d, v) for d, v in scored if sel[v] and (d, v) < rthr and (d, v) not in res])[:k]
     out = res if sel is not None else [(d, v) for d, v, _ in lst]
     ids = [v for _, v in out[:k]] + [-1] * (k - min(k, len(out)))
     return np.array(ids, np.int64), ndis, nhops
@@ -88,6 +116,11 @@ def test_sorted_list_formulation_equals_faiss_heaps(oracle_mod, seed):
             # forgetful visited set: identical ids, never fewer distance evaluations
             ids2, ndis2, _ = model_search(xb, g, cum, xq[i], k, ef, crd, max(ef, k) + 4 * M, None, dist)
             assert np.array_equal(ids2, Io[i]) and ndis2 >= ndis
+            # set-associative FIFO table, down to one that forgets nearly everything (list members too)
+            for buckets, ways in ((1, 2), (4, 4), (64, 8)):
+                ids3, ndis3, nhops3 = model_search(xb, g, cum, xq[i], k, ef, crd, None, None, dist,
+                                                   assoc=AssocVisited(buckets, ways))
+                assert np.array_equal(ids3, Io[i]) and ndis3 >= ndis and nhops3 == nhops
     # selector: filters results, not traversal
     member = rs.rand(n) < 0.2
     bm = np.packbits(member, bitorder="little")
@@ -95,6 +128,23 @@ def test_sorted_list_formulation_equals_faiss_heaps(oracle_mod, seed):
     for i in range(len(xq)):
         ids, ndis, nhops = model_search(xb, g, cum, xq[i], 10, 32, True, 40 + 4 * M, member, dist)
         assert np.array_equal(ids, Io[i]) and nhops == So[i, 1]
+        ids, ndis, nhops = model_search(xb, g, cum, xq[i], 10, 32, True, None, member, dist,
+                                        assoc=AssocVisited(4, 4))
+        assert np.array_equal(ids, Io[i]) and nhops == So[i, 1]
+
+
+def test_quotient_slots_name_ids_exactly():
+    """16-bit visited slots (beam.cuh, kVisitedAssoc16): h = (id * odd) mod 2^(b+16) is a bijection on
+    [0, 2^(b+16)), so (bucket = h >> 16, slot = h & 0xFFFF) identifies the id: two different vertices can
+    never be mistaken for each other, whatever the table size."""
+    for bbits in (2, 6, 8):
+        m = bbits + 16
+        ids = np.arange(1 << m, dtype=np.uint64)
+        h = (ids * np.uint64(2654435761)) & np.uint64((1 << m) - 1)
+        assert np.unique(h).size == ids.size
+        buckets = (h >> np.uint64(16)).astype(np.int64)
+        cnt = np.bincount(buckets, minlength=1 << bbits)
+        assert cnt.min() == cnt.max() == 1 << 16        # every bucket serves exactly 2^16 ids
 
 
 def _incremental_shrink(o, xb, owner, row, nver, src, max_size):

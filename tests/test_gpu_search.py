@@ -60,10 +60,32 @@ def test_distances_within_1e4_of_native_simd_oracle(oracle_mod, small_l2):
 
 def test_small_hash_forces_resets_but_not_result_changes(small_l2):
     idx = _gpu_from_oracle(small_l2["oracle"], small_l2["xb"], 16)
-    Do, Io = small_l2["oracle"].search(small_l2["xq"], 10, 128)
+    Do, Io, So = small_l2["oracle"].search(small_l2["xq"], 10, 128, stats=True)
     for hb in (8, 9, 10):
         D, I, S = idx.search(small_l2["xq"], 10, efSearch=128, stats=True, hash_bits=hb)
         assert np.array_equal(I, Io) and np.array_equal(D, Do)
+
+
+@pytest.mark.parametrize("W", [1, 4])
+def test_set_associative_visited_table_never_changes_results(small_l2, W):
+    """Default policy (visited_policy=2): 16-byte buckets with FIFO eviction. Down to a 64-byte table
+    (4 buckets: almost every vertex is forgotten and re-scored, list members included, so the merge's
+    identical-key rejection is exercised on nearly every hop) the ids and distances stay the oracle's;
+    the hop count is the oracle's; only ndis grows."""
+    idx = _gpu_from_oracle(small_l2["oracle"], small_l2["xb"], 16)
+    for ef in (16, 128):
+        Do, Io, So = small_l2["oracle"].search(small_l2["xq"], 10, ef, stats=True)
+        prev = None
+        for hb in (4, 6, 8, 11):
+            D, I, S = idx.search(small_l2["xq"], 10, efSearch=ef, stats=True, hash_bits=hb, visited_policy=2,
+                                 warps_per_query=W)
+            assert np.array_equal(I, Io) and np.array_equal(D, Do), (ef, hb)
+            assert np.array_equal(S[:, 1:], So[:, 1:]) and np.all(S[:, 0] >= So[:, 0])
+            if prev is not None:
+                assert S[:, 0].sum() <= prev          # a larger table forgets less
+            prev = S[:, 0].sum()
+        # 2 KB of 16-bit slots remember 1024 vertices: on this 4000-vertex graph that is nearly exact
+        assert S[:, 0].sum() <= 1.02 * So[:, 0].sum()
 
 
 def test_k_larger_than_efsearch_and_unbounded_steps(small_l2):
@@ -269,3 +291,101 @@ def test_rejected_import_keeps_the_old_index(small_l2):
     assert idx.ntotal == 4000
     D1, I1 = idx.search(small_l2["xq"], 10, efSearch=32)
     assert np.array_equal(I1, I0) and np.array_equal(D1, D0)
+
+
+@pytest.mark.parametrize("d,team", [(30, 8), (5, 8), (130, 16)])
+def test_dimension_not_a_multiple_of_four(oracle_mod, d, team):
+    """d % 4 != 0: rows are stored zero-padded to the next 16-byte chunk, which adds exact zeros to
+    L2 / IP — so results equal the oracle's on explicitly padded data, bit for bit, and equal the plain
+    (unpadded, native-order) oracle within the 1e-4 tolerance. reconstruct returns the caller's d."""
+    import hnsw_b200
+    dp = (d + 3) // 4 * 4
+    xb, xq = synthetic_dataset(d, 1500, 40)
+    pad = lambda a: np.ascontiguousarray(np.pad(a, ((0, 0), (0, dp - d))))
+    for metric in (1, 0):
+        o = oracle_mod.OracleHNSWFlat(dp, 8, metric)
+        o.set_team(team)
+        o.add(pad(xb))
+        g = o.export_graph()
+        idx = hnsw_b200.IndexHNSWFlat(d, 8, metric)
+        idx.import_graph(xb, g["levels"], g["neighbors"], g["entry_point"], g["max_level"])
+        Do, Io, So = o.search(pad(xq), 10, 48, stats=True)
+        D, I, S = idx.search(xq, 10, efSearch=48, stats=True, hash_bits=13)
+        assert np.array_equal(I, Io) and np.array_equal(D, Do) and np.array_equal(S, So)
+        assert np.array_equal(idx.reconstruct(7), xb[7]) and np.array_equal(idx.reconstruct_n(3, 5), xb[3:8])
+        # sequential GPU build on the odd-d data == oracle build on the padded data
+        b = hnsw_b200.IndexHNSWFlat(d, 8, metric)
+        b.set_build_params(max_batch=1)
+        b.add(xb)
+        assert np.array_equal(b.export_graph()["neighbors"], g["neighbors"])
+        nat = oracle_mod.OracleHNSWFlat(d, 8, metric)      # the caller's own d, CPU summation order
+        nat.import_graph(xb, g["levels"], g["neighbors"], g["entry_point"], g["max_level"])
+        Dn, In = nat.search(xq, 10, 48)
+        same = I == In
+        assert same.mean() > 0.99 and np.allclose(D[same], Dn[same], rtol=1e-4, atol=1e-6)
+
+
+def test_misaligned_device_queries_are_restaged(small_l2):
+    """search_device with a query pointer that is not 16-byte aligned (a tensor view at a 4-byte offset):
+    the rows are re-laid on the stream instead of being handed to the bulk copy (which would fault)."""
+    import torch
+    idx = _gpu_from_oracle(small_l2["oracle"], small_l2["xb"], 16)
+    xq = small_l2["xq"]
+    D0, I0 = idx.search(xq, 10, efSearch=48)
+    buf = torch.zeros(xq.size + 3, dtype=torch.float32, device="cuda")
+    for off in (1, 2, 3):
+        view = buf[off:off + xq.size]
+        view.copy_(torch.from_numpy(xq).reshape(-1).cuda())
+        assert view.data_ptr() % 16 != 0
+        D = torch.empty(len(xq), 10, device="cuda")
+        I = torch.empty(len(xq), 10, dtype=torch.int64, device="cuda")
+        idx.search_device(view.data_ptr(), len(xq), 10, D.data_ptr(), I.data_ptr(), efSearch=48)
+        idx.synchronize()
+        assert np.array_equal(I.cpu().numpy(), I0) and np.array_equal(D.cpu().numpy(), D0)
+    # host path, odd offset into a numpy buffer (pageable): staged copy re-aligns it
+    hb = np.zeros(xq.size + 1, np.float32)
+    hb[1:] = xq.reshape(-1)
+    D1, I1 = idx.search(hb[1:].reshape(xq.shape), 10, efSearch=48)
+    assert np.array_equal(I1, I0) and np.array_equal(D1, D0)
+
+
+def test_pageable_batch_is_chunked_over_lanes(small_l2):
+    """A pageable batch larger than one staging chunk goes round-robin over the context's lanes
+    (bh_index_search path 2), including more chunks than lanes and a ragged last chunk, with stats."""
+    o = small_l2["oracle"]
+    idx = _gpu_from_oracle(o, small_l2["xb"], 16)
+    rs = np.random.RandomState(11)
+    n = 4 * 32768 + 1234                                    # 5 chunks of 32768 (capped), ragged tail
+    xq = small_l2["xb"][rs.randint(0, 4000, n)] + 0.01 * rs.randn(n, 32).astype(np.float32)
+    o.threads = 8
+    Do, Io, So = o.search(xq, 5, 24, stats=True)
+    o.threads = 1
+    D, I, S = idx.search(xq, 5, efSearch=24, stats=True, hash_bits=12)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do) and np.array_equal(S, So)
+    D, I = idx.search(xq[:9000], 5, efSearch=24)            # 4 chunks of 2250
+    assert np.array_equal(I, Io[:9000]) and np.array_equal(D, Do[:9000])
+
+
+def test_concurrent_searches_on_one_handle(small_l2):
+    """faiss: search is const and thread-safe. Eight threads search one handle at once, each in its own
+    search context; every thread must get the single-threaded answer."""
+    import threading
+    idx = _gpu_from_oracle(small_l2["oracle"], small_l2["xb"], 16)
+    xq = small_l2["xq"]
+    want = {ef: idx.search(xq, 10, efSearch=ef) for ef in (16, 32, 64, 128)}
+    errs = []
+
+    def work(t):
+        try:
+            for it in range(20):
+                ef = (16, 32, 64, 128)[(t + it) % 4]
+                D, I = idx.search(xq, 10, efSearch=ef)
+                if not (np.array_equal(I, want[ef][1]) and np.array_equal(D, want[ef][0])):
+                    errs.append((t, it, ef))
+        except Exception as e:  # noqa: BLE001
+            errs.append((t, repr(e)))
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errs, errs[:3]
