@@ -26,6 +26,9 @@ class BuildParams(C.Structure):
                 ("warps_per_query", C.c_int32), ("hash_bits", C.c_int32), ("visited_policy", C.c_int32)]
 
 
+SHARDS_BLOB_BYTES = 160
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a into libb200hnsw.so (nvcc cross-compiles w/o a GPU)."""
     env = dict(os.environ)
@@ -77,6 +80,17 @@ _SIGS = {
     "bh_index_last_build_counters": (C.c_int, [_P, _P]),
     "bh_launch_count": (C.c_int64, []),
     "bh_merge_topk_device": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "bh_shards_create": (C.c_int, [C.POINTER(_P), _P, C.c_int, C.c_int, C.c_int64, C.c_int64]),
+    "bh_shards_free": (C.c_int, [_P]),
+    "bh_shards_export": (C.c_int, [_P, _P]),
+    "bh_shards_connect": (C.c_int, [_P, _P]),
+    "bh_shards_set_ntotals": (C.c_int, [_P, _P]),
+    "bh_shards_search_device": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, _P, C.POINTER(SearchParams)]),
+    "bh_shards_post": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.POINTER(SearchParams), C.c_int]),
+    "bh_shards_gather": (C.c_int, [_P, C.c_int64, C.c_int64, C.POINTER(_P)]),
+    "bh_shards_collect": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, C.c_int]),
+    "bh_shards_local_lists": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
+    "bh_shards_status": (C.c_int, [_P]),
     "bh_last_error": (C.c_char_p, []),
     "bh_version": (C.c_char_p, []),
 }

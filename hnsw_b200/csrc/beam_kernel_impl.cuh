@@ -13,6 +13,7 @@
 #include <cfloat>
 #include <climits>
 #include <cstdio>
+#include <mutex>
 
 namespace bh {
 
@@ -87,6 +88,13 @@ __global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, Bea
                         atomicAdd(t.build_counters + 3, (unsigned long long)st.nhops_up);
                     }
                 }
+            } else if (t.n_shard_out > 0) {
+                // sharded search: this shard's list goes straight into every rank's gather buffer (peer
+                // stores over NVLink; 8 bytes per result, one contiguous k*8-byte run per rank)
+                for (int i = lane; i < t.k; i += 32) {
+                    const unsigned long long kk = i < lsize ? key_clean(L[i]) : ~0ull;
+                    for (int p = 0; p < t.n_shard_out; p++) t.shard_out[p][(size_t)wi * t.k + i] = kk;
+                }
             } else {
                 const float pad = g.is_l2 ? FLT_MAX : -FLT_MAX;
                 for (int i = lane; i < t.k; i += 32) {
@@ -125,6 +133,10 @@ cudaError_t launch_one(const GraphView& g, const BeamTask& t, int num_sms, cudaS
                        int* grid_out) {
     auto kern = beam_kernel<TEAM, CPL, W, R, G, MINB, HALF>;
     const size_t smem = (size_t)G * group_smem_bytes(g.d, t.ef, 1 << t.hash_bits, g.deg0, t.sel ? t.k : 0);
+    // the dynamic-shared-memory limit is an attribute of the FUNCTION: concurrent searches with different
+    // efSearch would race between setting it and launching, so the pair is one critical section
+    static std::mutex launch_mu;
+    std::lock_guard<std::mutex> lk(launch_mu);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;

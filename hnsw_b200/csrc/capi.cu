@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unistd.h>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -286,9 +287,26 @@ struct bh_index {
         }
         if (req_bits > 0) {
             bits = std::min(std::max(req_bits, 4), 15);
+        } else if (const char* e = getenv("BH_VISITED_BITS")) {  // experiments only
+            bits = atoi(e);
         } else {
-            const char* e = getenv("BH_VISITED_BITS");  // experiments only
-            bits = e ? atoi(e) : std::min(std::max(ceil_log2((long long)ef * 4) + 2, 8), 12);
+            // Measured (profiles/r2_visited_sweep.jsonl, 1M x 128): residency beats the last few per cent
+            // of re-scoring — at ef=128 an 8 KB table re-scores 2 % but runs 13 % slower than a 4 KB one
+            // that re-scores 9 %, because only 20 instead of 24 queries stay resident per SM. So: the
+            // largest table up to 64 remembered vertices per list entry that still lets the full set of
+            // query groups (24 per SM; 16 for rows wider than 512 B, which run the 128-register variant)
+            // fit in shared memory; never below 2 KB.
+            const int ideal = std::min(std::max(ceil_log2((long long)ef * 8) + 2, 9), 13);
+            // (and not more than ~200 KB of the SM for the 24 groups: ef=384 with a 4 KB table fits 24
+            // groups in 217 KB but runs 12 % slower than with 2 KB — the L1 that is left matters)
+            const size_t groups = row_floats() / 4 > 32 ? 16 : 24;
+            const size_t budget = std::min<size_t>(smem_optin - (groups / 4) * 1024, 200 * 1024);
+            bits = 9;
+            for (int b = ideal; b > 9; b--)
+                if (groups * bh::beam_group_smem(dp, ef, b, deg0()) <= budget) {
+                    bits = b;
+                    break;
+                }
         }
         // 16-bit slots name an id exactly only while ntotal <= buckets * 2^16
         mode = (ntotal <= (1ll << (bits + 14))) ? bh::kVisitedAssoc16 : bh::kVisitedAssoc32;
@@ -460,7 +478,8 @@ struct CtxLease {  // gives the context back on every return path
 // One traversal launch: n queries at xq_d (device-addressable, 16-byte aligned rows of dp floats).
 int search_device_impl(const bh_index* h, cudaStream_t stream, int* counter, int64_t n, const float* xq_d,
                        int64_t k, float* D_d, int64_t* I_d, int32_t* stats_d, const bh_search_params* params,
-                       const uint8_t* sel_dev = nullptr) {
+                       const uint8_t* sel_dev = nullptr, int n_shard_out = 0,
+                       unsigned long long* const* shard_out = nullptr) {
     const int efS = (params && params->efSearch > 0) ? params->efSearch : h->efSearch;
     bool crd = h->check_relative_distance;
     if (params && params->check_relative_distance == 1) crd = true;
@@ -488,6 +507,8 @@ int search_device_impl(const bh_index* h, cudaStream_t stream, int* counter, int
     t.stats = stats_d;
     t.sel = sel_dev;
     t.counter = counter;
+    t.n_shard_out = n_shard_out;
+    for (int p = 0; p < n_shard_out; p++) t.shard_out[p] = shard_out[p];
     BH_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
     BH_CUDA(bh::launch_beam(h->view(), t, W, h->beam_variant(ef + rk, hb), h->num_sms, stream, nullptr));
     bh::count_launch();
@@ -1232,5 +1253,276 @@ int bh_merge_topk_device(int nshard, int64_t nq, int64_t k, int metric, const fl
                                   (cudaStream_t)stream));
     return 0;
 }
+
+}  // extern "C"
+
+// =================================================================== sharded search (one box)
+//
+// Replaces faiss::IndexShards(successive_ids = true) + merge_knn_results for the GPUs of
+// one box. Rank r owns the contiguous id range [offset_r, offset_r + ntotal_r) and an independent graph.
+// A search is collective: every rank calls it with the same queries; each rank's traversal kernel writes
+// its k results per query as packed 8-byte keys (distance bits, LOCAL id) straight into every rank's
+// gather buffer — peer memory over NVLink — a one-warp kernel then raises this rank's flag in every peer,
+// and the merge kernel waits for all flags and merges. No library collective, no host round trip, no
+// cross-stream wait: three launches on the index's stream.
+struct bh_shards {
+    bh_index* local = nullptr;
+    int rank = 0, nranks = 1;
+    int64_t max_q = 0, max_k = 0;
+    unsigned long long* arena = nullptr;  // [2 parities][nranks][max_q * max_k] packed keys, then the flags
+    size_t parity_elems = 0;              // nranks * max_q * max_k
+    unsigned long long* flags = nullptr;  // [nranks * kFlagStride], slot r = last epoch rank r published
+    unsigned long long* peer_arena[bh::kMaxPeers] = {};
+    bool peer_ipc[bh::kMaxPeers] = {};
+    int64_t ntotals[bh::kMaxPeers] = {};
+    bool connected = false;
+    unsigned long long epoch = 0;
+    int* status = nullptr;      // mapped host word: 1 = a peer did not publish within the timeout
+    int* status_dev = nullptr;
+    int timeout_ms = 20000;
+    std::mutex mu;
+};
+
+namespace {
+struct ShardBlob {  // BH_SHARDS_BLOB_BYTES
+    uint32_t magic;
+    int32_t rank, nranks, device;
+    int64_t pid, ntotal, max_q, max_k;
+    uint64_t raw_ptr;
+    cudaIpcMemHandle_t ipc;
+    char pad[BH_SHARDS_BLOB_BYTES - 4 - 12 - 32 - 8 - sizeof(cudaIpcMemHandle_t)];
+};
+static_assert(sizeof(ShardBlob) == BH_SHARDS_BLOB_BYTES, "blob layout");
+constexpr uint32_t kBlobMagic = 0x62685348u;
+
+unsigned long long* gather_slot(unsigned long long* arena, size_t parity_elems, int parity, int src_rank,
+                                int64_t n, int64_t k) {
+    // lists of one call are packed [src_rank][n][k] at the front of the parity's half
+    return arena + (size_t)parity * parity_elems + (size_t)src_rank * n * k;
+}
+}  // namespace
+
+extern "C" {
+
+int bh_shards_create(bh_shards** out, bh_index* local, int rank, int nranks, int64_t max_queries, int64_t max_k) {
+    if (!out) return fail("shards_create: out is null");
+    *out = nullptr;
+    if (!local) return fail("shards_create: null index");
+    if (nranks < 1 || nranks > bh::kMaxPeers || rank < 0 || rank >= nranks)
+        return fail("shards_create: need 0 <= rank < nranks <= 16");
+    if (max_queries < 1 || max_k < 1 || max_k > 4096) return fail("shards_create: bad max_queries / max_k");
+    BH_CUDA(cudaSetDevice(local->device));
+    std::unique_ptr<bh_shards> s(new bh_shards());
+    s->local = local;
+    s->rank = rank;
+    s->nranks = nranks;
+    s->max_q = max_queries;
+    s->max_k = max_k;
+    s->parity_elems = (size_t)nranks * max_queries * max_k;
+    const size_t flag_elems = (size_t)nranks * bh::kFlagStride;
+    const size_t bytes = (2 * s->parity_elems + flag_elems) * sizeof(unsigned long long);
+    BH_CUDA(cudaMalloc((void**)&s->arena, bytes));  // plain cudaMalloc: exportable with cudaIpcGetMemHandle
+    s->flags = s->arena + 2 * s->parity_elems;
+    cudaError_t e = cudaMemset(s->arena, 0, bytes);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->status, sizeof(int), cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        *s->status = 0;
+        e = cudaHostGetDevicePointer((void**)&s->status_dev, s->status, 0);
+    }
+    if (e != cudaSuccess) {
+        cudaFree(s->arena);
+        if (s->status) cudaFreeHost(s->status);
+        return fail(std::string("shards_create: ") + cudaGetErrorString(e));
+    }
+    s->peer_arena[rank] = s->arena;
+    s->ntotals[rank] = local->ntotal;
+    s->connected = nranks == 1;
+    *out = s.release();
+    return 0;
+}
+
+int bh_shards_free(bh_shards* s) {
+    if (!s) return 0;
+    cudaSetDevice(s->local->device);
+    cudaStreamSynchronize(s->local->stream);
+    for (int p = 0; p < s->nranks; p++)
+        if (s->peer_ipc[p] && s->peer_arena[p]) cudaIpcCloseMemHandle(s->peer_arena[p]);
+    if (s->arena) cudaFree(s->arena);
+    if (s->status) cudaFreeHost(s->status);
+    delete s;
+    return 0;
+}
+
+int bh_shards_export(bh_shards* s, void* blob) {
+    if (!s || !blob) return fail("shards_export: null argument");
+    BH_CUDA(cudaSetDevice(s->local->device));
+    ShardBlob b{};
+    b.magic = kBlobMagic;
+    b.rank = s->rank;
+    b.nranks = s->nranks;
+    b.device = s->local->device;
+    b.pid = (int64_t)getpid();
+    b.ntotal = s->local->ntotal;
+    b.max_q = s->max_q;
+    b.max_k = s->max_k;
+    b.raw_ptr = (uint64_t)(uintptr_t)s->arena;
+    BH_CUDA(cudaIpcGetMemHandle(&b.ipc, s->arena));
+    std::memcpy(blob, &b, sizeof(b));
+    return 0;
+}
+
+int bh_shards_connect(bh_shards* s, const void* blobs) {
+    if (!s || !blobs) return fail("shards_connect: null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    BH_CUDA(cudaSetDevice(s->local->device));
+    const ShardBlob* b = static_cast<const ShardBlob*>(blobs);
+    for (int p = 0; p < s->nranks; p++) {
+        if (b[p].magic != kBlobMagic || b[p].rank != p || b[p].nranks != s->nranks)
+            return fail("shards_connect: blob " + std::to_string(p) + " is not rank " + std::to_string(p) + "'s export");
+        if (b[p].max_q != s->max_q || b[p].max_k != s->max_k)
+            return fail("shards_connect: ranks were created with different max_queries / max_k");
+    }
+    for (int p = 0; p < s->nranks; p++) {
+        s->ntotals[p] = b[p].ntotal;
+        if (p == s->rank || s->peer_arena[p]) continue;  // re-connect only refreshes the shard sizes
+        if (b[p].pid == (int64_t)getpid()) {  // same process: the pointer itself, with peer access if needed
+            if (b[p].device != s->local->device) {
+                int can = 0;
+                BH_CUDA(cudaDeviceCanAccessPeer(&can, s->local->device, b[p].device));
+                if (!can) return fail("shards_connect: no peer access between the two devices");
+                const cudaError_t e = cudaDeviceEnablePeerAccess(b[p].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            s->peer_arena[p] = reinterpret_cast<unsigned long long*>((uintptr_t)b[p].raw_ptr);
+        } else {
+            void* ptr = nullptr;
+            const cudaError_t e = cudaIpcOpenMemHandle(&ptr, b[p].ipc, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(std::string("shards_connect: cudaIpcOpenMemHandle(rank ") + std::to_string(p) +
+                            "): " + cudaGetErrorString(e));
+            }
+            s->peer_arena[p] = static_cast<unsigned long long*>(ptr);
+            s->peer_ipc[p] = true;
+        }
+    }
+    s->connected = true;
+    return 0;
+}
+
+// first half: traverse the local shard, publish the packed lists (to every connected rank, or only to
+// this rank's own buffer when `publish_to_peers` is 0 — the caller then moves them, see bh_shards_gather)
+int bh_shards_post(bh_shards* s, int64_t n, const float* x, int64_t k, const bh_search_params* params,
+                   int publish_to_peers) {
+    if (!s) return fail("null shards handle");
+    const bh_index* h = s->local;
+    if (n < 1 || n > s->max_q || k < 1 || k > s->max_k) return fail("shards_post: n / k exceed max_queries / max_k");
+    if (!x) return fail("shards_post: null queries");
+    if (publish_to_peers && !s->connected) return fail("shards_post: not connected (bh_shards_connect)");
+    if (params && (params->stats || params->sel_bitmap)) return fail("shards_post: stats / selectors are per shard; not supported here");
+    std::lock_guard<std::mutex> slk(s->mu);
+    std::shared_lock<std::shared_mutex> lk(h->rw);
+    BH_CUDA(cudaSetDevice(h->device));
+    if (*s->status) return fail("sharded search: a peer did not publish its results in time (earlier call)");
+    CtxLease lease{h, acquire_ctx(h, true)};
+    if (!lease.c) return 1;
+    SearchCtx& c = *lease.c;
+    cudaStream_t st = c.lane[0].stream;
+    s->epoch++;
+    const int parity = (int)(s->epoch & 1);
+    unsigned long long* outs[bh::kMaxPeers];
+    int n_out = 0;
+    if (publish_to_peers) {
+        for (int p = 0; p < s->nranks; p++)
+            outs[n_out++] = gather_slot(s->peer_arena[p], s->parity_elems, parity, s->rank, n, k);
+    } else {
+        outs[n_out++] = gather_slot(s->arena, s->parity_elems, parity, s->rank, n, k);
+    }
+    if (h->ntotal == 0) {  // an empty shard publishes empty lists
+        for (int p = 0; p < n_out; p++) BH_CUDA(cudaMemsetAsync(outs[p], 0xFF, (size_t)n * k * 8, st));
+    } else {
+        if (h->d != h->dp || (reinterpret_cast<uintptr_t>(x) & 15) != 0) {
+            BH_CUDA(c.q_d.reserve((size_t)n * h->dp, st));
+            BH_CUDA(copy_rows_padded_async(c.q_d.p, x, n, h->d, h->dp, cudaMemcpyDeviceToDevice, st));
+            x = c.q_d.p;
+        }
+        if (int rc = search_device_impl(h, st, c.counters.p, n, x, k, nullptr, nullptr, nullptr, params, nullptr,
+                                        n_out, outs))
+            return rc;
+    }
+    if (publish_to_peers && s->nranks > 1) {
+        bh::PeerFlags pf{};
+        for (int p = 0; p < s->nranks; p++) pf.v[p] = s->peer_arena[p] + 2 * s->parity_elems;
+        BH_CUDA(bh::launch_shard_signal(s->nranks, s->rank, pf, s->epoch, st));
+    }
+    return 0;
+}
+
+// device pointer of the current call's gather buffer, [nranks][n][k] packed keys (this rank's slice at index
+// `rank`): a caller that exchanges with its own collective (e.g. one in-place NCCL all-gather of n*k*8 bytes
+// per rank) fills the other slices, then calls bh_shards_collect with wait_for_peers = 0
+int bh_shards_gather(bh_shards* s, int64_t n, int64_t k, void** ptr) {
+    if (!s || !ptr) return fail("null argument");
+    *ptr = gather_slot(s->arena, s->parity_elems, (int)(s->epoch & 1), 0, n, k);
+    return 0;
+}
+
+// second half: wait for every rank's lists of the current call (wait_for_peers), merge, write D / I with
+// global ids (local id + the owning shard's offset, successive_ids)
+int bh_shards_collect(bh_shards* s, int64_t n, int64_t k, float* distances, int64_t* labels, int wait_for_peers) {
+    if (!s) return fail("null shards handle");
+    const bh_index* h = s->local;
+    if (n < 1 || n > s->max_q || k < 1 || k > s->max_k) return fail("shards_collect: n / k exceed max_queries / max_k");
+    if (!distances || !labels) return fail("shards_collect: null buffer");
+    std::lock_guard<std::mutex> slk(s->mu);
+    BH_CUDA(cudaSetDevice(h->device));
+    bh::ShardOffsets off{};
+    int64_t acc = 0;
+    for (int p = 0; p < s->nranks; p++) {
+        off.v[p] = acc;
+        acc += s->ntotals[p];
+    }
+    const bool wait = wait_for_peers && s->nranks > 1;
+    BH_CUDA(bh::launch_merge_packed(s->nranks, n, (int)k, h->metric == BH_METRIC_L2,
+                                    gather_slot(s->arena, s->parity_elems, (int)(s->epoch & 1), 0, n, k), off,
+                                    distances, labels, wait ? s->flags : nullptr, s->epoch, s->status_dev,
+                                    s->timeout_ms, h->stream));
+    return 0;
+}
+
+// this rank's own lists of the current call as (D, I) with LOCAL ids (device buffers [n][k])
+int bh_shards_local_lists(bh_shards* s, int64_t n, int64_t k, float* distances, int64_t* labels) {
+    if (!s || !distances || !labels) return fail("null argument");
+    const bh_index* h = s->local;
+    BH_CUDA(cudaSetDevice(h->device));
+    BH_CUDA(bh::launch_unpack(gather_slot(s->arena, s->parity_elems, (int)(s->epoch & 1), s->rank, n, k), n * k,
+                              h->metric == BH_METRIC_L2, distances, labels, h->stream));
+    return 0;
+}
+
+// the collective call: post + collect. x / distances / labels are device pointers on this rank's GPU;
+// enqueued on the local index's stream, returns without synchronising.
+int bh_shards_search_device(bh_shards* s, int64_t n, const float* x, int64_t k, float* distances, int64_t* labels,
+                            const bh_search_params* params) {
+    if (!s) return fail("null shards handle");
+    if (n < 0 || k <= 0) return fail("search: need n >= 0 and k > 0");
+    for (int64_t i0 = 0; i0 < n; i0 += s->max_q) {  // batches beyond max_queries: one exchange per slice
+        const int64_t m = std::min<int64_t>(s->max_q, n - i0);
+        if (int rc = bh_shards_post(s, m, x + (size_t)i0 * s->local->d, k, params, 1)) return rc;
+        if (int rc = bh_shards_collect(s, m, k, distances + (size_t)i0 * k, labels + (size_t)i0 * k, 1)) return rc;
+    }
+    return 0;
+}
+
+int bh_shards_set_ntotals(bh_shards* s, const int64_t* ntotals) {
+    if (!s || !ntotals) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    for (int p = 0; p < s->nranks; p++) s->ntotals[p] = ntotals[p];
+    return 0;
+}
+
+int bh_shards_status(bh_shards* s) { return s ? *s->status : -1; }
 
 }  // extern "C"

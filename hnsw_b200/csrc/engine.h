@@ -8,6 +8,8 @@
 
 namespace bh {
 
+constexpr int kMaxPeers = 16;  // GPUs of one box that exchange results by peer stores
+
 // One batch of traversal work for beam_kernel.
 struct BeamTask {
     // search mode (items == nullptr)
@@ -30,6 +32,11 @@ struct BeamTask {
     unsigned long long* build_counters;  // device [6] or null: {ndis0, nhops0, ndis_up, nhops_up, sel_rows, bl_rows}
     const uint8_t* sel;  // device IDSelectorBitmap over the shard's ids, or null (search mode only)
     int* counter;    // device work counter, zeroed before launch
+    // sharded search (search mode only): instead of D / I the epilogue publishes each query's k results as
+    // packed (order-preserving distance bits << 32 | local id) keys, ~0 = empty, straight into the gather
+    // buffer of every rank of the box — peer memory over NVLink — at shard_out[p][item * k + i]
+    int n_shard_out;
+    unsigned long long* shard_out[kMaxPeers];
 };
 
 size_t beam_group_smem(int d, int ef, int hash_bits, int deg, int rk = 0);
@@ -71,6 +78,25 @@ struct ShardOffsets {  // passed by value in the kernel parameters: no allocatio
 cudaError_t launch_merge_topk(int nshard, int64_t nq, int k, int is_l2, const float* D_all,
                               const int64_t* I_all, const ShardOffsets& id_offsets, float* D_out,
                               int64_t* I_out, cudaStream_t stream);
+
+// Sharded exchange, packed form (merge_kernel.cu). `gather` = this rank's [nshard][nq][k] packed keys (each
+// list written by its owner's traversal kernel, see BeamTask::shard_out). signal: store `epoch` into slot
+// `my_rank` of every peer's flag array (release, system scope). merge: wait until all nshard local flags
+// reach `epoch` (when flags != nullptr), then the same rank-by-counting merge as launch_merge_topk.
+// `status` (mapped host memory) is set to 1 if a peer never arrived within timeout_ms.
+struct PeerFlags {
+    unsigned long long* v[kMaxPeers];
+};
+constexpr int kFlagStride = 16;  // flags are 128 bytes apart
+cudaError_t launch_shard_signal(int nshard, int my_rank, const PeerFlags& peer_flags, unsigned long long epoch,
+                                cudaStream_t stream);
+cudaError_t launch_merge_packed(int nshard, int64_t nq, int k, int is_l2, const unsigned long long* gather,
+                                const ShardOffsets& id_offsets, float* D_out, int64_t* I_out,
+                                const unsigned long long* flags, unsigned long long epoch, int* status,
+                                int timeout_ms, cudaStream_t stream);
+// packed keys [n] -> (D fp32, I int64 local ids) (a rank's own lists, for callers that want them)
+cudaError_t launch_unpack(const unsigned long long* keys, int64_t n, int is_l2, float* D, int64_t* I,
+                          cudaStream_t stream);
 
 // ---- storage conversion (merge_kernel.cu): fp32 rows <-> fp16 rows, element-wise RNE / exact widening
 cudaError_t launch_f32_to_f16(const float* src, void* dst, size_t n, cudaStream_t stream);

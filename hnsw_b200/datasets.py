@@ -28,8 +28,11 @@ def synthetic_dataset(d: int, nb: int, nq: int, d1: int = 10, seed: int = 1338,
 
 
 def synthetic_dataset_torch(d: int, nb: int, nq: int, d1: int = 32, seed: int = 1338,
-                            normalize: bool = False, device="cuda", chunk: int = 1 << 20):
-    """Same recipe on a torch device, generated in row chunks (fits 100M x 96)."""
+                            normalize: bool = False, device="cuda", chunk: int = 1 << 20,
+                            keep_rows: tuple[int, int] | None = None):
+    """Same recipe on a torch device, generated in row chunks (fits 100M x 96).
+    keep_rows=(lo, hi): every row is still drawn (so the stream is the same on every rank) but only
+    database rows [lo, hi) and the queries are kept — a rank's shard of an N-shard database."""
     import torch
 
     g = torch.Generator(device=device)
@@ -37,15 +40,22 @@ def synthetic_dataset_torch(d: int, nb: int, nq: int, d1: int = 32, seed: int = 
     proj = torch.rand(d1, d, generator=g, device=device, dtype=torch.float32)
     scale = torch.rand(d, generator=g, device=device, dtype=torch.float32) * 4 + 0.1
     n = nb + nq
-    out = torch.empty(n, d, device=device, dtype=torch.float32)
+    lo, hi = keep_rows if keep_rows is not None else (0, nb)
+    xb = torch.empty(hi - lo, d, device=device, dtype=torch.float32)
+    xq = torch.empty(nq, d, device=device, dtype=torch.float32)
     for i0 in range(0, n, chunk):
         i1 = min(n, i0 + chunk)
         z = torch.randn(i1 - i0, d1, generator=g, device=device, dtype=torch.float32)
         x = torch.sin((z @ proj) * scale)
         if normalize:
             x = x / x.norm(dim=1, keepdim=True).clamp_min(1e-20)
-        out[i0:i1] = x
-    return out[:nb], out[nb:]
+        a, b = max(i0, lo), min(i1, hi)          # database rows of this chunk that are kept
+        if a < b:
+            xb[a - lo:b - lo] = x[a - i0:b - i0]
+        a, b = max(i0, nb), i1                     # query rows of this chunk
+        if a < b:
+            xq[a - nb:b - nb] = x[a - i0:b - i0]
+    return xb, xq
 
 
 def exact_knn_torch(xb, xq, k: int, inner_product: bool = False, chunk: int = 1 << 18):

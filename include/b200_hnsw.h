@@ -148,6 +148,44 @@ int bh_merge_topk_device(int nshard, int64_t nq, int64_t k, int metric, const fl
                          const int64_t* I_all, const int64_t* id_offsets /*host, [nshard]*/,
                          float* D_out, int64_t* I_out, void* stream);
 
+/* -- sharded search over the GPUs of one box (replaces faiss::IndexShards(successive_ids=true) and its
+ *    merge_knn_results; faiss/IndexShards.cpp) ------------------------------------------------------
+ * One bh_shards per rank (= per GPU / per local index); the ranks may live in one process or in one
+ * process each. Rank r owns global ids [sum(ntotal_0..r-1), +ntotal_r). Bootstrap: every rank exports
+ * a fixed-size blob, the caller moves the blobs between ranks over any channel it owns (MPI,
+ * a socket, a file), every rank connects with all of them (CUDA IPC across processes, plain
+ * peer access inside one). A search is collective — every rank calls it with the same queries: the
+ * traversal kernel's epilogue stores each query's k results as 8-byte (distance bits, local id) keys
+ * straight into every rank's gather buffer over NVLink, a one-warp kernel raises a flag in every
+ * peer, and the merge kernel waits for all flags and merges: no library collective, no host round
+ * trip. max_queries / max_k size the gather buffers (larger batches are sliced). */
+typedef struct bh_shards bh_shards;
+#define BH_SHARDS_BLOB_BYTES 160
+int bh_shards_create(bh_shards** out, bh_index* local, int rank, int nranks, int64_t max_queries,
+                     int64_t max_k);
+int bh_shards_free(bh_shards* s);
+int bh_shards_export(bh_shards* s, void* blob /* [BH_SHARDS_BLOB_BYTES] */);
+int bh_shards_connect(bh_shards* s, const void* blobs /* [nranks][BH_SHARDS_BLOB_BYTES], rank order */);
+/* shard sizes for the id offsets, if the shards grew after connect (host array [nranks]) */
+int bh_shards_set_ntotals(bh_shards* s, const int64_t* ntotals);
+/* replaces IndexShards::search; device pointers on this rank's GPU, enqueued on the local index's
+ * stream, no synchronisation; labels are global ids */
+int bh_shards_search_device(bh_shards* s, int64_t n, const float* x, int64_t k, float* distances,
+                            int64_t* labels, const bh_search_params* params);
+/* the two halves of a search, for callers that exchange the lists themselves or emulate ranks:
+ * post = traverse + publish (publish_to_peers = 0: only into this rank's own gather buffer);
+ * gather = device pointer of this call's [nranks][n][k] packed gather buffer;
+ * collect = (wait for every rank's flag if wait_for_peers) + merge;
+ * local_lists = this rank's own lists of the current call, local ids */
+int bh_shards_post(bh_shards* s, int64_t n, const float* x, int64_t k, const bh_search_params* params,
+                   int publish_to_peers);
+int bh_shards_gather(bh_shards* s, int64_t n, int64_t k, void** ptr);
+int bh_shards_collect(bh_shards* s, int64_t n, int64_t k, float* distances, int64_t* labels,
+                      int wait_for_peers);
+int bh_shards_local_lists(bh_shards* s, int64_t n, int64_t k, float* distances, int64_t* labels);
+/* 0 = fine; 1 = a peer did not publish within the timeout (results of that call are undefined) */
+int bh_shards_status(bh_shards* s);
+
 const char* bh_last_error(void);
 const char* bh_version(void);
 

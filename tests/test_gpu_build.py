@@ -176,8 +176,22 @@ def test_fp16_storage_bit_exact_vs_oracle_half_mode(oracle_mod, d, M, team, metr
     b.hnsw.efConstruction = 32
     b.add(xb)
     assert_graph_invariants(b.export_graph(), M, n)
-    with pytest.raises(RuntimeError):
-        hnsw_b200.IndexHNSWFlat(12, 4, 1, storage="fp16")      # d % 8 != 0
+    # d % 8 != 0: fp16 rows are zero-padded to whole 16-byte chunks; sequential build == oracle half mode
+    # on explicitly padded data
+    x12, q12 = synthetic_dataset(12, 600, 20)
+    pad = lambda a: np.ascontiguousarray(np.pad(a, ((0, 0), (0, 4))))
+    o12 = oracle_mod.OracleHNSWFlat(16, 4, 1)
+    o12.set_team(8)
+    o12.set_half_storage(True)
+    o12.add(pad(x12))
+    i12 = hnsw_b200.IndexHNSWFlat(12, 4, 1, storage="fp16")
+    i12.set_build_params(max_batch=1)
+    i12.add(x12)
+    assert np.array_equal(i12.export_graph()["neighbors"], o12.export_graph()["neighbors"])
+    Do, Io = o12.search(pad(q12), 5, 32)
+    D, I = i12.search(q12, 5, efSearch=32)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do)
+    assert np.array_equal(i12.reconstruct(3), x12[3].astype(np.float16).astype(np.float32))
 
 
 def test_rejected_add_leaves_index_untouched(oracle_mod):

@@ -389,3 +389,89 @@ def test_concurrent_searches_on_one_handle(small_l2):
     [t.start() for t in ths]
     [t.join() for t in ths]
     assert not errs, errs[:3]
+
+
+def _host_merge(Ds, Is, offs, metric):
+    """Exact merge of per-shard sorted lists: by distance, ties by shard then position (stable)."""
+    allD = np.concatenate(Ds, axis=1)
+    allI = np.concatenate([np.where(I >= 0, I + o, -1) for I, o in zip(Is, offs)], axis=1)
+    order = np.argsort(allD if metric == 1 else -allD, axis=1, kind="stable")[:, :Ds[0].shape[1]]
+    return np.take_along_axis(allD, order, 1), np.take_along_axis(allI, order, 1)
+
+
+@pytest.mark.parametrize("metric", [1, 0])
+def test_shards_cabi_two_ranks_emulated_on_one_gpu(metric):
+    """bh_shards_* with two ranks living in ONE process on ONE GPU (the same-process branch of connect):
+    each rank's traversal kernel stores its packed lists into both gather buffers, the flags are raised,
+    and each rank's merge equals the exact host-side merge of the two per-shard results. The two halves
+    (post / collect) are called separately and the streams are synchronised in between, so no kernel ever
+    spins on a kernel of the same GPU. Also the caller-moves-the-lists variant (publish_to_peers = 0)."""
+    import ctypes as C
+    import torch
+    import hnsw_b200
+    from hnsw_b200 import _lib
+    L = _lib.lib()
+    d, M, k, nq = 32, 16, 10, 300
+    xb, xq = synthetic_dataset(d, 5000, nq, normalize=(metric == 0))
+    cut = [0, 2600, 5000]
+    idxs = []
+    for r in range(2):
+        ix = hnsw_b200.IndexHNSWFlat(d, M, metric)
+        ix.add(xb[cut[r]:cut[r + 1]])
+        idxs.append(ix)
+    per = [ix.search(xq, k, efSearch=48) for ix in idxs]
+    Dw, Iw = _host_merge([p[0] for p in per], [p[1] for p in per], cut[:2], metric)
+    hs = []
+    for r in range(2):
+        s = C.c_void_p()
+        _lib.check(L.bh_shards_create(C.byref(s), idxs[r]._h, r, 2, 512, 16))
+        hs.append(s)
+    try:
+        blobs = (C.c_ubyte * (2 * _lib.SHARDS_BLOB_BYTES))()
+        for r in range(2):
+            _lib.check(L.bh_shards_export(hs[r], C.byref(blobs, r * _lib.SHARDS_BLOB_BYTES)))
+        for r in range(2):
+            _lib.check(L.bh_shards_connect(hs[r], blobs))
+        q = torch.from_numpy(xq).cuda()
+        p = _lib.SearchParams(48, 0, 0, 0, None, None, 0, 0, 0)
+        for rep in range(3):                       # three epochs: both parities of the gather buffer
+            for r in range(2):
+                _lib.check(L.bh_shards_post(hs[r], nq, q.data_ptr(), k, C.byref(p), 1))
+            for r in range(2):
+                idxs[r].synchronize()              # both ranks have published: collect cannot spin
+            outs = []
+            for r in range(2):
+                D = torch.empty(nq, k, device="cuda")
+                I = torch.empty(nq, k, dtype=torch.int64, device="cuda")
+                _lib.check(L.bh_shards_collect(hs[r], nq, k, D.data_ptr(), I.data_ptr(), 1))
+                Dl = torch.empty(nq, k, device="cuda")
+                Il = torch.empty(nq, k, dtype=torch.int64, device="cuda")
+                _lib.check(L.bh_shards_local_lists(hs[r], nq, k, Dl.data_ptr(), Il.data_ptr()))
+                idxs[r].synchronize()
+                assert L.bh_shards_status(hs[r]) == 0
+                assert np.array_equal(Dl.cpu().numpy(), per[r][0]) and np.array_equal(Il.cpu().numpy(), per[r][1])
+                outs.append((D.cpu().numpy(), I.cpu().numpy()))
+            for D, I in outs:
+                assert np.array_equal(I, Iw) and np.array_equal(D, Dw)
+        # the caller exchanges the lists itself (what the NCCL fallback does with one all-gather)
+        for r in range(2):
+            _lib.check(L.bh_shards_post(hs[r], nq, q.data_ptr(), k, C.byref(p), 0))
+            idxs[r].synchronize()
+        views = []
+        for r in range(2):
+            gp = C.c_void_p()
+            _lib.check(L.bh_shards_gather(hs[r], nq, k, C.byref(gp)))
+            from hnsw_b200.sharded import _device_view_i64
+            views.append(_device_view_i64(gp.value, 2 * nq * k, torch.device("cuda", 0)))
+        views[0][nq * k:].copy_(views[1][nq * k:])
+        views[1][:nq * k].copy_(views[0][:nq * k])
+        torch.cuda.synchronize()
+        for r in range(2):
+            D = torch.empty(nq, k, device="cuda")
+            I = torch.empty(nq, k, dtype=torch.int64, device="cuda")
+            _lib.check(L.bh_shards_collect(hs[r], nq, k, D.data_ptr(), I.data_ptr(), 0))
+            idxs[r].synchronize()
+            assert np.array_equal(I.cpu().numpy(), Iw) and np.array_equal(D.cpu().numpy(), Dw)
+    finally:
+        for s in hs:
+            L.bh_shards_free(s)
