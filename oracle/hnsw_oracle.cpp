@@ -714,6 +714,18 @@ int orc_add(void* p, int64_t n, const float* x, int nthreads, int32_t* order_out
     return 0;
 }
 
+// add() with caller-supplied levels (level + 1 per point), as faiss allows by filling hnsw.levels before
+// add: prepare_level_tab then skips the random draw (A.7). Used by the hand-worked golden test.
+int orc_add_preset(void* p, int64_t n, const float* x, const int* levels, int nthreads) {
+    Oracle* o = static_cast<Oracle*>(p);
+    if (n < 0 || (size_t)o->ntotal != o->levels.size()) return 1;
+    for (int64_t i = 0; i < n; i++) {
+        if (levels[i] < 1 || levels[i] > (int)o->assign_probas.size()) return 2;
+    }
+    o->levels.insert(o->levels.end(), levels, levels + n);
+    return orc_add(p, n, x, nthreads, nullptr);
+}
+
 // Draw levels for the next n points exactly as add() would (advances the index RNG) —
 // lets a test feed the same levels to the GPU engine.
 void orc_peek_levels(void* p, int64_t n, int* levels_out) {

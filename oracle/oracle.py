@@ -69,6 +69,8 @@ def _load(path: str | None = None) -> C.CDLL:
     L.orc_get_cum_nneighbor.argtypes = [C.c_void_p, _i32p]
     L.orc_add.argtypes = [C.c_void_p, C.c_int64, _f32p, C.c_int, C.c_void_p]
     L.orc_add.restype = C.c_int
+    L.orc_add_preset.argtypes = [C.c_void_p, C.c_int64, _f32p, _i32p, C.c_int]
+    L.orc_add_preset.restype = C.c_int
     L.orc_peek_levels.argtypes = [C.c_void_p, C.c_int64, _i32p]
     L.orc_search.argtypes = [C.c_void_p, C.c_int64, _f32p, C.c_int64, _f32p, _i64p, C.c_int,
                              C.c_int, C.c_void_p]
@@ -162,6 +164,15 @@ class OracleHNSWFlat:
         if rc:
             raise RuntimeError(f"orc_add rc={rc}")
         return order
+
+    def add_with_levels(self, x: np.ndarray, levels):
+        """add() with preset levels (level + 1 per row), faiss's `hnsw.levels` preset."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        lv = np.ascontiguousarray(levels, np.int32)
+        assert x.ndim == 2 and x.shape[1] == self.d and lv.shape == (x.shape[0],)
+        rc = self._L.orc_add_preset(self._h, x.shape[0], x, lv, int(self.threads))
+        if rc:
+            raise RuntimeError(f"orc_add_preset rc={rc}")
 
     def peek_levels(self, n: int) -> np.ndarray:
         out = np.empty(n, np.int32)
