@@ -80,6 +80,9 @@ _SIGS = {
     "bh_index_last_build_counters": (C.c_int, [_P, _P]),
     "bh_launch_count": (C.c_int64, []),
     "bh_merge_topk_device": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "bh_selector_range_to_bitmap": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _P]),
+    "bh_selector_batch_to_bitmap": (C.c_int, [C.c_int64, C.c_int64, _P, _P]),
+    "bh_selector_not": (C.c_int, [C.c_int64, _P]),
     "bh_shards_create": (C.c_int, [C.POINTER(_P), _P, C.c_int, C.c_int, C.c_int64, C.c_int64]),
     "bh_shards_free": (C.c_int, [_P]),
     "bh_shards_export": (C.c_int, [_P, _P]),

@@ -1109,6 +1109,27 @@ int bh_index_reconstruct_n(const bh_index* h, int64_t i0, int64_t ni, float* out
     return 0;
 }
 
+int bh_selector_range_to_bitmap(int64_t ntotal, int64_t imin, int64_t imax, uint8_t* bitmap) {
+    if (ntotal < 0 || !bitmap) return fail("selector: bad arguments");
+    std::memset(bitmap, 0, (size_t)((ntotal + 7) / 8));
+    for (int64_t i = std::max<int64_t>(imin, 0); i < std::min(imax, ntotal); i++) bitmap[i >> 3] |= (uint8_t)(1u << (i & 7));
+    return 0;
+}
+int bh_selector_batch_to_bitmap(int64_t ntotal, int64_t n, const int64_t* ids, uint8_t* bitmap) {
+    if (ntotal < 0 || n < 0 || !bitmap || (n > 0 && !ids)) return fail("selector: bad arguments");
+    std::memset(bitmap, 0, (size_t)((ntotal + 7) / 8));
+    for (int64_t j = 0; j < n; j++)
+        if (ids[j] >= 0 && ids[j] < ntotal) bitmap[ids[j] >> 3] |= (uint8_t)(1u << (ids[j] & 7));
+    return 0;
+}
+int bh_selector_not(int64_t ntotal, uint8_t* bitmap) {
+    if (ntotal < 0 || !bitmap) return fail("selector: bad arguments");
+    const int64_t nb = (ntotal + 7) / 8;
+    for (int64_t b = 0; b < nb; b++) bitmap[b] = (uint8_t)~bitmap[b];
+    if (ntotal & 7) bitmap[nb - 1] &= (uint8_t)((1u << (ntotal & 7)) - 1u);  // ids >= ntotal stay non-members
+    return 0;
+}
+
 int64_t bh_index_ntotal(const bh_index* h) { return h ? h->ntotal : -1; }
 int bh_index_d(const bh_index* h) { return h ? h->d : -1; }
 int bh_index_M(const bh_index* h) { return h ? h->M : -1; }

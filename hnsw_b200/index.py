@@ -15,6 +15,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import BuildParams, SearchParams
+from .selectors import SearchParametersHNSW
 
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
@@ -138,6 +139,12 @@ class IndexHNSWFlat:
                 if not (isinstance(a, np.ndarray) and a.dtype == dt and a.shape == (nq, k) and a.flags.c_contiguous):
                     raise ValueError(f"out= needs C-contiguous ({nq}, {k}) float32 / int64 arrays")
         st = np.zeros((nq, 4), np.int32) if stats else None
+        if isinstance(params, SearchParametersHNSW):   # faiss-style per-call parameters
+            crd = params.check_relative_distance
+            if params.sel is not None:
+                sel_bitmap = params.sel.to_bitmap(self.ntotal)
+            params = SearchParams(int(params.efSearch or efSearch or 0), 0 if crd is None else (1 if crd else 2),
+                                  int(warps_per_query), int(hash_bits), None, None, 0, int(visited_policy), 0)
         if params is None:
             params = SearchParams(int(efSearch or 0), 0, int(warps_per_query), int(hash_bits), None, None, 0,
                                   int(visited_policy), 0)

@@ -100,6 +100,16 @@ int bh_index_reconstruct(const bh_index* h, int64_t key, float* out);
 /* replaces faiss::Index::reconstruct_n(i0, ni, recons) */
 int bh_index_reconstruct_n(const bh_index* h, int64_t i0, int64_t ni, float* out);
 
+/* -- other faiss IDSelectors, converted on the host into the bitmap form above ------------------
+ * bitmap: caller-allocated, (ntotal + 7) / 8 bytes; pass it as bh_search_params.sel_bitmap.
+ * replaces faiss::IDSelectorRange(imin, imax): member iff imin <= id < imax */
+int bh_selector_range_to_bitmap(int64_t ntotal, int64_t imin, int64_t imax, uint8_t* bitmap);
+/* replaces faiss::IDSelectorBatch(n, ids) / IDSelectorArray: member iff id is listed (ids outside
+ * [0, ntotal) are ignored, as they can never be returned) */
+int bh_selector_batch_to_bitmap(int64_t ntotal, int64_t n, const int64_t* ids, uint8_t* bitmap);
+/* replaces faiss::IDSelectorNot: flips membership of every id < ntotal, in place */
+int bh_selector_not(int64_t ntotal, uint8_t* bitmap);
+
 /* -- fields (faiss: index.d, index.ntotal, index.hnsw.efSearch, …) ---------------- */
 int64_t bh_index_ntotal(const bh_index* h);
 int bh_index_d(const bh_index* h);
