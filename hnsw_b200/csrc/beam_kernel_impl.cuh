@@ -20,6 +20,9 @@ namespace bh {
 template <int TEAM, int CPL, int W, int R, int G, int MINB, bool HALF>
 __global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, BeamTask t) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // Nothing this grid reads is produced by the launch before it, so the next search launch on the stream
+    // may begin as soon as SM slots free up (no-op unless that launch asked for programmatic serialisation).
+    if (t.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int grp = warp / W;
@@ -148,6 +151,19 @@ cudaError_t launch_one(const GraphView& g, const BeamTask& t, int num_sms, cudaS
     if (grid > groups_needed) grid = groups_needed;
     if (grid < 1) grid = 1;
     if (grid_out) *grid_out = (int)grid;
+    if (t.pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(32 * W * G);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kern, g, t);
+    }
     kern<<<(unsigned)grid, 32 * W * G, smem, stream>>>(g, t);
     return cudaGetLastError();
 }

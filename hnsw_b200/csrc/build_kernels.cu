@@ -314,6 +314,141 @@ __global__ void __launch_bounds__(64) select_and_link_kernel(GraphView g, BuildB
     }
 }
 
+// ---- forward links + back-edge staging, CTA-cooperative: NW warps share one (point, level) item ------
+//
+// The selection heuristic is ~8 500 pairwise distances per item (200 candidates x the ~40 vertices kept so
+// far) and strictly sequential in the candidates, so one warp per item is latency-bound: at 33 KB of kept-
+// vector cache per warp only ~6 warps fit on an SM and each stalls on its own fmaf chains (round 1:
+// issue-active 39 %). Here the NW warps of a CTA hold the SAME 32/TEAM candidates (one per team) and split
+// the KEPT set: warp w scores kept blocks w, w+NW, ... (4 kept per block), the per-team "rejected" bits are
+// OR-ed through shared memory with one CTA barrier per step, and the short acceptance phase (appending
+// to the kept set in candidate order, testing later candidates of the same step against a newly kept one)
+// is replayed identically by every warp. One kept-vector cache per CTA, NW x the warps per SM, 1/NW of the
+// scan latency per step. Same comparisons on the same values as the one-warp version => same graph.
+template <int TEAM, int CPL, int NW, bool KV, bool HALF>
+__global__ void __launch_bounds__(32 * NW) select_and_link_coop_kernel(GraphView g, BuildBatch b) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int TPW = 32 / TEAM;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lit = lane % TEAM, team = lane / TEAM;
+    unsigned long long* kept_key = reinterpret_cast<unsigned long long*>(smem_raw);     // [deg0]
+    unsigned* flags = reinterpret_cast<unsigned*>(smem_raw + (size_t)g.deg0 * 8);       // [2][NW]
+    float4* kvec = reinterpret_cast<float4*>(smem_raw + (size_t)g.deg0 * 8 + 64);       // [deg0][nchunk] (KV)
+    const float4* __restrict__ vecs = reinterpret_cast<const float4*>(g.vecs);
+    const bool is_l2 = g.is_l2 != 0;
+    const int nchunk = g.nchunk;
+    for (int item = blockIdx.x; item < b.n_items; item += gridDim.x) {
+        const int4 it = __ldg(b.items + item);
+        const int pt = it.x, level = it.y;
+        int deg;
+        int32_t* row = row_ptr_rw(g, pt, level, deg);
+        const unsigned long long* cand = b.cand_lists + (size_t)item * b.efc;
+        const int n = b.cand_counts[item];
+        int K = 0;
+        const unsigned long long* kept = kept_key;
+        const bool verified = n >= deg;
+        if (!verified) {  // shrink_neighbor_list returns early: keep everything
+            K = n;
+            kept = cand;
+        } else {
+            TeamVec<TEAM, CPL, HALF> nxt;
+            unsigned long long nxt_key = ~0ull;
+            auto fetch = [&](int c0) {
+                const int c = c0 + team;
+                const bool valid = c < n;
+                nxt_key = valid ? cand[c] : ~0ull;
+                nxt.load(vecs + (size_t)(valid ? key_id(nxt_key) : 0) * nchunk, nchunk, lit, valid);
+            };
+            auto kept_row = [&](int j) -> const float4* {
+                return KV ? kvec + (size_t)j * nchunk : vecs + (size_t)key_id(kept_key[j]) * nchunk;
+            };
+            fetch(0);
+            int parity = 0;
+            for (int c0 = 0; c0 < n && K < deg; c0 += TPW, parity ^= 1) {
+                const TeamVec<TEAM, CPL, HALF> v = nxt;
+                const unsigned long long key = nxt_key;
+                const bool valid = c0 + team < n;
+                if (c0 + TPW < n) fetch(c0 + TPW);  // in flight while this group is tested
+                const uint32_t id = key_id(key);
+                const float dq = key_dist(key);
+                bool bad = !valid;
+                // this warp's share of the kept set: blocks of four, round-robin over the warps
+                const int nfull = K >> 2;
+                for (int blk = wid; blk < nfull; blk += NW) {
+                    if (__all_sync(0xffffffffu, bad)) break;
+                    const int j = blk << 2;
+                    float duv[4];
+                    v.dist4(kept_row(j), kept_row(j + 1), kept_row(j + 2), kept_row(j + 3), nchunk, lit, is_l2, duv);
+                    if (duv[0] < dq || duv[1] < dq || duv[2] < dq || duv[3] < dq) bad = true;
+                }
+                if (wid == nfull % NW) {  // the partial last block
+                    for (int j = nfull << 2; j < K; j++) {
+                        if (__all_sync(0xffffffffu, bad)) break;
+                        const float duv = v.dist(kept_row(j), nchunk, lit, is_l2);
+                        if (duv < dq) bad = true;
+                    }
+                }
+                const unsigned mine = __ballot_sync(0xffffffffu, bad);
+                if (lane == 0) flags[parity * NW + wid] = mine;
+                __syncthreads();
+                unsigned all = 0;
+#pragma unroll
+                for (int w2 = 0; w2 < NW; w2++) all |= flags[parity * NW + w2];
+                bad = (all >> (team * TEAM)) & 1u;
+                // acceptance in candidate order — every warp replays it identically (same values written)
+                for (int t = 0; t < TPW; t++) {
+                    const int bad_t = __shfl_sync(0xffffffffu, (int)bad, t * TEAM);
+                    if (bad_t) continue;
+                    if (team == t) {
+                        if (lit == 0) kept_key[K] = key;
+                        if (KV) {
+#pragma unroll
+                            for (int cc = 0; cc < CPL; cc++) {
+                                const int chunk = cc * TEAM + lit;
+                                if (chunk < nchunk) kvec[(size_t)K * nchunk + chunk] = v.raw[cc];
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    K++;
+                    if (K >= deg) break;
+                    if (t + 1 < TPW) {
+                        const uint32_t id_t = __shfl_sync(0xffffffffu, id, t * TEAM);
+                        const float4* u = KV ? kvec + (size_t)(K - 1) * nchunk : vecs + (size_t)id_t * nchunk;
+                        const float duv = v.dist(u, nchunk, lit, is_l2);
+                        if (team > t && duv < dq) bad = true;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            *nver_ptr(g, b, pt, level) = verified ? (uint8_t)K : (uint8_t)0;
+            if (b.build_counters && verified) atomicAdd(b.build_counters + 4, (unsigned long long)n);  // candidate rows read
+        }
+        // faiss pops link_targets farthest-first: row[i] = kept[K-1-i]
+        for (int i = threadIdx.x; i < g.deg0; i += blockDim.x) {
+            const int e = item * g.deg0 + i;
+            if (i < K) {
+                const unsigned long long key = kept[K - 1 - i];
+                const int o = (int)key_id(key);
+                row[i] = o;
+                const int slot = row_slot(g, b.n_level0, o, level);
+                b.edge_src[e] = pt;
+                b.edge_dst[e] = o;
+                b.edge_level[e] = level;
+                b.edge_dist[e] = key_dist(key);
+                b.edge_dst_slot[e] = slot;
+                b.edge_next[e] = atomicExch(b.slot_head + slot, e);
+            } else {
+                if (i < deg) row[i] = -1;
+                b.edge_dst_slot[e] = -1;
+            }
+        }
+        __syncthreads();  // kept_key / kvec are reused by the next item
+    }
+}
+
 // ---- App. A.11 add_link(dst ← src) for every staged back-edge ------------------------
 //
 // Full rows re-run shrink_neighbor_list on the 2M+1 candidates. Done naively that is ~2000
@@ -526,18 +661,23 @@ cudaError_t launch_build_pair(bool backlinks, const GraphView& g, const BuildBat
     const int wpb = 2;
     cudaError_t e;
     if (!backlinks) {
-        const bool kvec = (size_t)(g.deg0 + 1) * g.nchunk * 16 <= 48 * 1024;
-        const size_t smem = wpb * warp_smem_bytes(g.nchunk * 4, g.deg0, kvec);
-        auto ks = select_and_link_kernel<TEAM, CPL, HALF>;
-        e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        int occ = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ks, 32 * wpb, smem);
-        long long grid = (long long)num_sms * (occ < 1 ? 1 : occ);
-        const long long need = (b.n_items + wpb - 1) / wpb;
-        if (grid > need) grid = need;
-        if (grid < 1) grid = 1;
-        ks<<<(unsigned)grid, 32 * wpb, smem, stream>>>(g, b, (int)kvec);
+        constexpr int NW = 4;
+        const size_t kv_bytes = (size_t)g.deg0 * g.nchunk * 16;
+        const bool kvec = kv_bytes <= 64 * 1024;  // kept-vector cache per CTA; wider rows re-read kept vectors (L2)
+        const size_t smem = (size_t)g.deg0 * 8 + 64 + (kvec ? kv_bytes : 0);
+        auto launch = [&](auto ks) -> cudaError_t {
+            cudaError_t e2 = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e2 != cudaSuccess) return e2;
+            int occ = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ks, 32 * NW, smem);
+            long long grid = (long long)num_sms * (occ < 1 ? 1 : occ);
+            if (grid > b.n_items) grid = b.n_items;
+            if (grid < 1) grid = 1;
+            ks<<<(unsigned)grid, 32 * NW, smem, stream>>>(g, b);
+            return cudaGetLastError();
+        };
+        return kvec ? launch(select_and_link_coop_kernel<TEAM, CPL, NW, true, HALF>)
+                    : launch(select_and_link_coop_kernel<TEAM, CPL, NW, false, HALF>);
     } else {
         const size_t smem = wpb * warp_smem_bytes(g.nchunk * 4, g.deg0, false, b.max_special);
         auto kb = backlink_kernel<TEAM, CPL, HALF>;

@@ -1,5 +1,7 @@
 """Deep100M-shape sharded config (BASELINE configs[3]): N x (n_shard x d) database, one sub-graph per
-GPU, queries broadcast, NCCL all-gather of per-shard top-k, warp merge kernel. Launch with torchrun.
+GPU, queries broadcast, per-shard top-k exchanged by the C-ABI's bh_shards_* path (peer stores over NVLink +
+flag barrier + merge kernel; falls back to one packed NCCL all-gather), and the same shard searched alone as
+the efficiency denominator. Launch with torchrun.
 Each rank generates its own shard on the device (same recipe, per-rank seed offset in the latent
 draw but ONE shared projection, so all shards are samples of the same distribution)."""
 import argparse, json, os, sys, time
@@ -77,11 +79,25 @@ for ef in [int(e) for e in a.efs.split(",")]:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     Ih = I.cpu().numpy()
     rec = float(np.mean([len(set(Ih[i].tolist()) & set(gt[i].tolist())) for i in range(a.nq)])) / a.k
+    # the same shard alone: no exchange, no merge
+    D1 = torch.empty(a.nq, a.k, device=dev); I1 = torch.empty(a.nq, a.k, dtype=torch.int64, device=dev)
+    st1 = torch.cuda.ExternalStream(sh.local.stream_ptr, device=dev)
+    for _ in range(3):
+        sh.local.search_device(xq.data_ptr(), a.nq, a.k, D1.data_ptr(), I1.data_ptr(), efSearch=ef)
+    sh.local.synchronize(); dist.barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(st1)
+    for _ in range(a.steps):
+        sh.local.search_device(xq.data_ptr(), a.nq, a.k, D1.data_ptr(), I1.data_ptr(), efSearch=ef)
+    f1.record(st1); sh.local.synchronize()
+    ms1 = torch.tensor([f0.elapsed_time(f1) / a.steps], device=dev)
+    dist.all_reduce(ms1, op=dist.ReduceOp.MAX)
     rows.append({"efSearch": ef, "ms_per_batch": round(float(ms.item()), 3), "qps": round(a.nq / float(ms.item()) * 1e3),
-                 "recall_at_10": round(rec, 4)})
+                 "recall_at_10": round(rec, 4), "ms_shard_alone_max_over_ranks": round(float(ms1.item()), 3),
+                 "efficiency_vs_single_shard": round(float(ms1.item()) / float(ms.item()), 4)})
 if rank == 0:
     print(json.dumps({"config": f"sharded {world} x {a.n_shard} x {a.d} fp32 {'IP' if a.ip else 'L2'}, M={a.M} efC={a.efc}, {a.nq} queries broadcast, "
-                                f"all-gather {a.nq * a.k * 12} B/rank + merge kernel",
+                                f"exchange = {sh.exchange_kind} ({a.nq * a.k * 8} B/rank) + merge kernel",
                       "db_vectors": world * a.n_shard, "n_gpus": world,
                       "build_s": round(t_build, 2), "build_vectors_per_s_total": round(world * a.n_shard / t_build),
                       "search": rows}), flush=True)
