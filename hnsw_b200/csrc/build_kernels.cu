@@ -44,12 +44,17 @@ struct TeamVec {
         return is_l2 ? acc : -acc;
     }
     // Same arithmetic as Beam::compute_dists: one fmaf chain per lane, xor-butterfly over the team.
+    // (rows of exactly TEAM * CPL chunks — d = 128, 96, ... — take the predicate-free path)
     __device__ __forceinline__ float dist(const float4* row, int nchunk, int lit, bool is_l2) const {
+        return nchunk == TEAM * CPL ? dist_t<true>(row, nchunk, lit, is_l2) : dist_t<false>(row, nchunk, lit, is_l2);
+    }
+    template <bool FULL>
+    __device__ __forceinline__ float dist_t(const float4* row, int nchunk, int lit, bool is_l2) const {
         float acc = 0.f;
 #pragma unroll
         for (int c = 0; c < CPL; c++) {
             const int chunk = c * TEAM + lit;
-            const float4 u = chunk < nchunk ? row[chunk] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 u = (FULL || chunk < nchunk) ? row[chunk] : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 uf[ES];
             chunk_to_f32<HALF>(u, uf);
 #pragma unroll
@@ -70,6 +75,15 @@ struct TeamVec {
     __device__ __forceinline__ void dist4(const float4* r0, const float4* r1, const float4* r2,
                                           const float4* r3, int nchunk, int lit, bool is_l2,
                                           float (&out)[4]) const {
+        if (nchunk == TEAM * CPL)
+            dist4_t<true>(r0, r1, r2, r3, nchunk, lit, is_l2, out);
+        else
+            dist4_t<false>(r0, r1, r2, r3, nchunk, lit, is_l2, out);
+    }
+    template <bool FULL>
+    __device__ __forceinline__ void dist4_t(const float4* r0, const float4* r1, const float4* r2,
+                                            const float4* r3, int nchunk, int lit, bool is_l2,
+                                            float (&out)[4]) const {
         const float4* rows[4] = {r0, r1, r2, r3};
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -78,7 +92,7 @@ struct TeamVec {
             float4 u[4];
 #pragma unroll
             for (int p = 0; p < 4; p++)
-                u[p] = chunk < nchunk ? rows[p][chunk] : make_float4(0.f, 0.f, 0.f, 0.f);
+                u[p] = (FULL || chunk < nchunk) ? rows[p][chunk] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int p = 0; p < 4; p++) {
                 float4 uf[ES];
