@@ -491,9 +491,20 @@ __global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b,
     const int nwarps = gridDim.x * (blockDim.x >> 5);
     const int n_edges = b.n_items * g.deg0;
     (void)use_kvec;
-    for (int e0 = blockIdx.x * (blockDim.x >> 5) + wib; e0 < n_edges; e0 += nwarps) {
-        const int slot = b.edge_dst_slot[e0];
-        if (slot < 0 || b.edge_next[e0] != -1) continue;  // only the tail of a row's list owns it
+    // 32 edge slots per step, one per lane (coalesced); the warp then works through the slots among them
+    // that own a row's pending list — only the TAIL of a list (next == -1) owns it
+    for (int base = (blockIdx.x * (blockDim.x >> 5) + wib) * 32; base < n_edges; base += nwarps * 32) {
+      int slot_l = -1;
+      if (base + lane < n_edges) {
+          slot_l = b.edge_dst_slot[base + lane];
+          if (slot_l >= 0 && b.edge_next[base + lane] != -1) slot_l = -1;
+      }
+      unsigned owners = __ballot_sync(0xffffffffu, slot_l >= 0);
+      while (owners) {
+        const int ol = __ffs(owners) - 1;
+        owners &= owners - 1;
+        const int e0 = base + ol;
+        const int slot = __shfl_sync(0xffffffffu, slot_l, ol);
         // collect the row's pending edges (pushed in arbitrary order); applied in edge-index order
         int c = 0, head = -1;
         if (lane == 0) {
@@ -666,6 +677,7 @@ __global__ void __launch_bounds__(64) backlink_kernel(GraphView g, BuildBatch b,
             __syncwarp();
         }
         if (lane == 0 && nv != nv0) *nvp = (uint8_t)nv;
+      }
     }
 }
 
