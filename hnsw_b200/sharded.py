@@ -57,8 +57,8 @@ class ShardedIndexHNSWFlat:
     def _free(self):
         s = getattr(self, "_s", None)
         if s:
-            from . import _lib
-            try:
+            try:  # (at interpreter shutdown even the import may fail)
+                from . import _lib
                 _lib.lib().bh_shards_free(s)
             except Exception:
                 pass

@@ -61,3 +61,26 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or fn == "Makefile":
                 txt = open(os.path.join(dp, fn)).read()
                 assert not bad.search(txt), f"{fn} reaches into oracle/"
+
+
+def test_header_is_plain_c_and_the_cpp_example_links(tmp_path):
+    """include/b200_hnsw.h must compile as C99 (it is a C-ABI), and examples/index_shards_b200.cpp — the
+    faiss::IndexShards replacement written against the C-ABI only — must compile and link against the
+    built library (running it needs GPUs)."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PATH="/usr/bin:/bin:" + os.environ.get("PATH", ""))
+    r = subprocess.run(["gcc", "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", _lib.HEADER_PATH],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    cuda = "/usr/local/cuda"
+    if not (shutil.which("g++", path=env["PATH"]) and os.path.exists(os.path.join(cuda, "include", "cuda_runtime.h"))):
+        pytest.skip("no g++ / CUDA headers")
+    _lib.lib()
+    out = str(tmp_path / "index_shards_b200")
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
+                        os.path.join(root, "examples", "index_shards_b200.cpp"), "-L", os.path.join(root, "hnsw_b200"),
+                        "-lb200hnsw", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lpthread", "-o", out],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr

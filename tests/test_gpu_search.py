@@ -475,3 +475,35 @@ def test_shards_cabi_two_ranks_emulated_on_one_gpu(metric):
     finally:
         for s in hs:
             L.bh_shards_free(s)
+
+
+def test_faiss_selector_family_equals_the_bitmap_form(small_l2):
+    """IDSelectorRange / IDSelectorBatch / IDSelectorNot and SearchParametersHNSW(sel=...): converted on the
+    host into IDSelectorBitmap (bh_selector_*), so the result must equal the oracle's run with that bitmap."""
+    import hnsw_b200
+    o = small_l2["oracle"]
+    idx = _gpu_from_oracle(o, small_l2["xb"], 16)
+    n = 4000
+    rs = np.random.RandomState(3)
+    ids = rs.choice(n, 700, replace=False)
+    cases = [
+        (hnsw_b200.IDSelectorRange(500, 1700), (np.arange(n) >= 500) & (np.arange(n) < 1700)),
+        (hnsw_b200.IDSelectorBatch(ids), np.isin(np.arange(n), ids)),
+        (hnsw_b200.IDSelectorNot(hnsw_b200.IDSelectorRange(100, 3900)), (np.arange(n) < 100) | (np.arange(n) >= 3900)),
+        (hnsw_b200.IDSelectorBitmap(np.packbits(np.arange(n) % 3 == 0, bitorder="little")), np.arange(n) % 3 == 0),
+    ]
+    for sel, member in cases:
+        assert np.array_equal(np.unpackbits(sel.to_bitmap(n), bitorder="little")[:n].astype(bool), member)
+        bm = np.packbits(member, bitorder="little")
+        Do, Io = o.search(small_l2["xq"], 10, 64, sel_bitmap=bm)
+        D, I = idx.search(small_l2["xq"], 10, params=hnsw_b200.SearchParametersHNSW(efSearch=64, sel=sel))
+        assert np.array_equal(I, Io) and np.array_equal(D, Do)
+        assert member[I[I >= 0]].all()
+    # SearchParametersHNSW without a selector: per-call efSearch / check_relative_distance
+    o.set_check_relative_distance(False)
+    try:
+        Do, Io = o.search(small_l2["xq"], 10, 24)
+    finally:
+        o.set_check_relative_distance(True)
+    D, I = idx.search(small_l2["xq"], 10, params=hnsw_b200.SearchParametersHNSW(efSearch=24, check_relative_distance=False))
+    assert np.array_equal(I, Io) and np.array_equal(D, Do)
