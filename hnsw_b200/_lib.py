@@ -94,6 +94,8 @@ _SIGS = {
     "bh_shards_collect": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, C.c_int]),
     "bh_shards_local_lists": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "bh_shards_status": (C.c_int, [_P]),
+    "bh_shards_set_pipelined": (C.c_int, [_P, C.c_int]),
+    "bh_shards_join": (C.c_int, [_P, _P]),
     "bh_last_error": (C.c_char_p, []),
     "bh_version": (C.c_char_p, []),
 }

@@ -124,7 +124,7 @@ struct Beam {
                 q[c][0] = ok ? s.qbuf[chunk] : z;
             } else {
                 if (stored_row) {
-                    chunk_to_f32<true>(ok ? s.qbuf[chunk] : z, q[c]);
+                    chunk_to_f32<true>(ok ? s.qbuf[chunk] : z, q[c], g.half);
                 } else {
                     q[c][0] = ok ? s.qbuf[2 * chunk] : z;
                     q[c][1] = ok ? s.qbuf[2 * chunk + 1] : z;
@@ -188,7 +188,7 @@ struct Beam {
 #pragma unroll
                 for (int c = 0; c < CPL; c++) {
                     float4 xf[ES];
-                    chunk_to_f32<HALF>(x[k][c], xf);
+                    chunk_to_f32<HALF>(x[k][c], xf, g.half);
 #pragma unroll
                     for (int e = 0; e < ES; e++) acc4(acc, q[c][e], xf[e], l2);
                 }

@@ -28,16 +28,16 @@ struct TeamVec {
     static constexpr int ES = HALF ? 2 : 1;
     float4 raw[CPL];
     float4 f[CPL][ES];
-    __device__ __forceinline__ void set_raw(int c, const float4& v) {
+    __device__ __forceinline__ void set_raw(int c, const float4& v, int fmt) {
         raw[c] = v;
-        chunk_to_f32<HALF>(v, f[c]);
+        chunk_to_f32<HALF>(v, f[c], fmt);
     }
     // Load this lane's slice of a stored vector (generic pointer: global or shared).
-    __device__ __forceinline__ void load(const float4* row, int nchunk, int lit, bool valid) {
+    __device__ __forceinline__ void load(const float4* row, int nchunk, int lit, bool valid, int fmt) {
 #pragma unroll
         for (int c = 0; c < CPL; c++) {
             const int chunk = c * TEAM + lit;
-            set_raw(c, (valid && chunk < nchunk) ? row[chunk] : make_float4(0.f, 0.f, 0.f, 0.f));
+            set_raw(c, (valid && chunk < nchunk) ? row[chunk] : make_float4(0.f, 0.f, 0.f, 0.f), fmt);
         }
     }
     __device__ __forceinline__ float reduce(float acc, bool is_l2) const {
@@ -47,18 +47,18 @@ struct TeamVec {
     }
     // Same arithmetic as Beam::compute_dists: one fmaf chain per lane, xor-butterfly over the team.
     // (rows of exactly TEAM * CPL chunks — d = 128, 96, ... — take the predicate-free path)
-    __device__ __forceinline__ float dist(const float4* row, int nchunk, int lit, bool is_l2) const {
-        return nchunk == TEAM * CPL ? dist_t<true>(row, nchunk, lit, is_l2) : dist_t<false>(row, nchunk, lit, is_l2);
+    __device__ __forceinline__ float dist(const float4* row, int nchunk, int lit, bool is_l2, int fmt) const {
+        return nchunk == TEAM * CPL ? dist_t<true>(row, nchunk, lit, is_l2, fmt) : dist_t<false>(row, nchunk, lit, is_l2, fmt);
     }
     template <bool FULL>
-    __device__ __forceinline__ float dist_t(const float4* row, int nchunk, int lit, bool is_l2) const {
+    __device__ __forceinline__ float dist_t(const float4* row, int nchunk, int lit, bool is_l2, int fmt) const {
         float acc = 0.f;
 #pragma unroll
         for (int c = 0; c < CPL; c++) {
             const int chunk = c * TEAM + lit;
             const float4 u = (FULL || chunk < nchunk) ? row[chunk] : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 uf[ES];
-            chunk_to_f32<HALF>(u, uf);
+            chunk_to_f32<HALF>(u, uf, fmt);
 #pragma unroll
             for (int e = 0; e < ES; e++) acc4(acc, uf[e], f[c][e], is_l2);
         }
@@ -76,16 +76,16 @@ struct TeamVec {
     // Four independent pairs at once (same per-pair arithmetic; the four fmaf chains interleave).
     __device__ __forceinline__ void dist4(const float4* r0, const float4* r1, const float4* r2,
                                           const float4* r3, int nchunk, int lit, bool is_l2,
-                                          float (&out)[4]) const {
+                                          float (&out)[4], int fmt) const {
         if (nchunk == TEAM * CPL)
-            dist4_t<true>(r0, r1, r2, r3, nchunk, lit, is_l2, out);
+            dist4_t<true>(r0, r1, r2, r3, nchunk, lit, is_l2, out, fmt);
         else
-            dist4_t<false>(r0, r1, r2, r3, nchunk, lit, is_l2, out);
+            dist4_t<false>(r0, r1, r2, r3, nchunk, lit, is_l2, out, fmt);
     }
     template <bool FULL>
     __device__ __forceinline__ void dist4_t(const float4* r0, const float4* r1, const float4* r2,
                                             const float4* r3, int nchunk, int lit, bool is_l2,
-                                            float (&out)[4]) const {
+                                            float (&out)[4], int fmt) const {
         const float4* rows[4] = {r0, r1, r2, r3};
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -98,7 +98,7 @@ struct TeamVec {
 #pragma unroll
             for (int p = 0; p < 4; p++) {
                 float4 uf[ES];
-                chunk_to_f32<HALF>(u[p], uf);
+                chunk_to_f32<HALF>(u[p], uf, fmt);
 #pragma unroll
                 for (int e = 0; e < ES; e++) acc4(acc[p], uf[e], f[c][e], is_l2);
             }
@@ -141,9 +141,9 @@ __device__ int heuristic(const GraphView& g, const unsigned long long* cand, int
         nxt_key = valid ? cand[c] : ~0ull;
         if (STAGED) {
             nxt_slot = valid ? cand_slot[c] : 0;
-            nxt.load(stage + (size_t)nxt_slot * g.nchunk, g.nchunk, lit, valid);
+            nxt.load(stage + (size_t)nxt_slot * g.nchunk, g.nchunk, lit, valid, g.half);
         } else {
-            nxt.load(vecs + (size_t)(valid ? key_id(nxt_key) : 0) * g.nchunk, g.nchunk, lit, valid);
+            nxt.load(vecs + (size_t)(valid ? key_id(nxt_key) : 0) * g.nchunk, g.nchunk, lit, valid, g.half);
         }
     };
     fetch(0);
@@ -165,12 +165,12 @@ __device__ int heuristic(const GraphView& g, const unsigned long long* cand, int
         for (; j + 4 <= K; j += 4) {  // four kept vectors per iteration: independent fmaf chains
             if (__all_sync(0xffffffffu, bad)) break;
             float duv[4];
-            v.dist4(kept_row(j), kept_row(j + 1), kept_row(j + 2), kept_row(j + 3), g.nchunk, lit, is_l2, duv);
+            v.dist4(kept_row(j), kept_row(j + 1), kept_row(j + 2), kept_row(j + 3), g.nchunk, lit, is_l2, duv, g.half);
             if (duv[0] < dq || duv[1] < dq || duv[2] < dq || duv[3] < dq) bad = true;
         }
         for (; j < K; j++) {
             if (__all_sync(0xffffffffu, bad)) break;
-            const float duv = v.dist(kept_row(j), g.nchunk, lit, is_l2);
+            const float duv = v.dist(kept_row(j), g.nchunk, lit, is_l2, g.half);
             if (duv < dq) bad = true;
         }
         for (int t = 0; t < TPW; t++) {
@@ -198,7 +198,7 @@ __device__ int heuristic(const GraphView& g, const unsigned long long* cand, int
                 const float4* u = STAGED ? stage + (size_t)slot_t * g.nchunk
                                          : (kvec ? kvec + (size_t)(K - 1) * g.nchunk
                                                  : vecs + (size_t)id_t * g.nchunk);
-                const float duv = v.dist(u, g.nchunk, lit, is_l2);
+                const float duv = v.dist(u, g.nchunk, lit, is_l2, g.half);
                 if (team > t && duv < dq) bad = true;
             }
         }
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(32 * NW) select_and_link_coop_kernel(GraphView
                 const int c = c0 + team;
                 const bool valid = c < n;
                 nxt_key = valid ? cand[c] : ~0ull;
-                nxt.load(vecs + (size_t)(valid ? key_id(nxt_key) : 0) * nchunk, nchunk, lit, valid);
+                nxt.load(vecs + (size_t)(valid ? key_id(nxt_key) : 0) * nchunk, nchunk, lit, valid, g.half);
             };
             auto kept_row = [&](int j) -> const float4* {
                 return KV ? kvec + (size_t)j * nchunk : vecs + (size_t)key_id(kept_key[j]) * nchunk;
@@ -394,13 +394,13 @@ __global__ void __launch_bounds__(32 * NW) select_and_link_coop_kernel(GraphView
                     if (__all_sync(0xffffffffu, bad)) break;
                     const int j = blk << 2;
                     float duv[4];
-                    v.dist4(kept_row(j), kept_row(j + 1), kept_row(j + 2), kept_row(j + 3), nchunk, lit, is_l2, duv);
+                    v.dist4(kept_row(j), kept_row(j + 1), kept_row(j + 2), kept_row(j + 3), nchunk, lit, is_l2, duv, g.half);
                     if (duv[0] < dq || duv[1] < dq || duv[2] < dq || duv[3] < dq) bad = true;
                 }
                 if (wid == nfull % NW) {  // the partial last block
                     for (int j = nfull << 2; j < K; j++) {
                         if (__all_sync(0xffffffffu, bad)) break;
-                        const float duv = v.dist(kept_row(j), nchunk, lit, is_l2);
+                        const float duv = v.dist(kept_row(j), nchunk, lit, is_l2, g.half);
                         if (duv < dq) bad = true;
                     }
                 }
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(32 * NW) select_and_link_coop_kernel(GraphView
                     if (t + 1 < TPW) {
                         const uint32_t id_t = __shfl_sync(0xffffffffu, id, t * TEAM);
                         const float4* u = KV ? kvec + (size_t)(K - 1) * nchunk : vecs + (size_t)id_t * nchunk;
-                        const float duv = v.dist(u, nchunk, lit, is_l2);
+                        const float duv = v.dist(u, nchunk, lit, is_l2, g.half);
                         if (team > t && duv < dq) bad = true;
                     }
                 }
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(64, MINB) backlink_kernel(GraphView g, BuildBa
             // full row: the deg+1 candidates fight it out (shrink_neighbor_list).
             // candidate index a: 0 = src, 1 + p = row member at position p
             if (!q_loaded) {
-                q.load(vecs + (size_t)dst * g.nchunk, g.nchunk, lit, true);
+                q.load(vecs + (size_t)dst * g.nchunk, g.nchunk, lit, true, g.half);
                 q_loaded = true;
             }
             const int n = deg + 1;
@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(64, MINB) backlink_kernel(GraphView g, BuildBa
                     if (si < ns) {
                         const int id = si == 0 ? src : w.rowid[nv + si - 1];
                         TeamVec<TEAM, CPL, HALF> tv;
-                        tv.load(vecs + (size_t)id * g.nchunk, g.nchunk, lit, true);
+                        tv.load(vecs + (size_t)id * g.nchunk, g.nchunk, lit, true, g.half);
 #pragma unroll
                         for (int c2 = 0; c2 < CPL; c2++) {
                             const int chunk = c2 * TEAM + lit;
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(64, MINB) backlink_kernel(GraphView g, BuildBa
                     for (int c2 = 0; c2 < CPL; c2++) {
                         const int chunk = c2 * TEAM + lit;
                         x[k2].set_raw(c2, (cid[k2] >= 0 && chunk < g.nchunk) ? ldg_stream(rowv + chunk)
-                                                                            : make_float4(0.f, 0.f, 0.f, 0.f));
+                                                                            : make_float4(0.f, 0.f, 0.f, 0.f), g.half);
                     }
                 }
 #pragma unroll
@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(64, MINB) backlink_kernel(GraphView g, BuildBa
                         w.cand_a[a] = a == 0 ? pack_key(d_src, (uint32_t)src) : pack_key(dd, (uint32_t)cid[k2]);
                     if (incremental) {
                         for (int si = 0; si < ns; si++) {
-                            const float ds = x[k2].dist(w.spec_vec + (size_t)si * g.nchunk, g.nchunk, lit, is_l2);
+                            const float ds = x[k2].dist(w.spec_vec + (size_t)si * g.nchunk, g.nchunk, lit, is_l2, g.half);
                             if (cid[k2] >= 0 && lit == 0) w.dsx[si * stride + a] = ds;
                         }
                     }

@@ -184,7 +184,7 @@ struct bh_index {
     int dp = 0;  // stored row width in elements: d rounded up to a whole number of 16-byte chunks (4 fp32 /
                  // 8 fp16), the tail zero-filled — adds exact zeros to L2 and IP, so distances are unchanged
     int M = 0, metric = BH_METRIC_L2, device = 0;
-    int storage = BH_STORAGE_F32;  // BH_STORAGE_F16: rows held as fp16 (opt-in)
+    int storage = BH_STORAGE_F32;  // BH_STORAGE_F16 / BH_STORAGE_BF16: rows held in 16 bits (opt-in)
     int efSearch = 16, efConstruction = 40;  // faiss HNSW defaults (App. A.1)
     bool check_relative_distance = true;
     bh_build_params bp{0, 0, 0, 0, 0};
@@ -226,7 +226,8 @@ struct bh_index {
     DevBuf<float> e_dist;
 
     int deg0() const { return 2 * M; }
-    bool half() const { return storage == BH_STORAGE_F16; }
+    bool half() const { return storage != BH_STORAGE_F32; }  // 16-bit rows
+    int fmt16() const { return storage == BH_STORAGE_BF16 ? 2 : 1; }
     int row_floats() const { return half() ? dp / 2 : dp; }  // stored row size in 4-byte units
     void set_padded_dim() { dp = half() ? (d + 7) / 8 * 8 : (d + 3) / 4 * 4; }
     mutable DevBuf<float> conv_d;                           // fp32 staging for fp16 conversion
@@ -240,7 +241,7 @@ struct bh_index {
         g.upper_nbr = upper_nbr.p;
         g.d = dp;
         g.nchunk = row_floats() / 4;
-        g.half = half() ? 1 : 0;
+        g.half = half() ? fmt16() : 0;
         g.deg0 = deg0();
         g.degU = M;
         g.entry_point = entry_point;
@@ -442,7 +443,7 @@ int upload_vectors(bh_index* h, int64_t n0, int64_t n, const float* x) {
     for (int64_t i0 = 0; i0 < n; i0 += chunk) {
         const int64_t m = std::min(chunk, n - i0);
         BH_CUDA(copy_rows_padded_async(h->conv_d.p, x + (size_t)i0 * d, m, d, dp, cudaMemcpyHostToDevice, h->stream));
-        BH_CUDA(bh::launch_f32_to_f16(h->conv_d.p, dst + (size_t)(n0 + i0) * dp * 2, (size_t)m * dp, h->stream));
+        BH_CUDA(bh::launch_f32_to_f16(h->conv_d.p, dst + (size_t)(n0 + i0) * dp * 2, (size_t)m * dp, h->stream, h->fmt16()));
     }
     return 0;
 }
@@ -484,6 +485,16 @@ struct CtxLease {  // gives the context back on every return path
         h->pool_cv.notify_all();
     }
 };
+
+// Work counter for an overlapping launch on the context's lane 0: the next slot of the ring; entering a
+// half of the ring re-zeroes the OTHER half (its launches are >= 32 calls old) with an ordinary memset.
+int next_ring_counter(SearchCtx& c, cudaStream_t st, int** counter) {
+    const unsigned seq = c.ring_seq++;
+    const unsigned slot = seq % SearchCtx::kRing, half = SearchCtx::kRing / 2;
+    if (slot % half == 0) BH_CUDA(cudaMemsetAsync(c.ring.p + (slot == 0 ? half : 0), 0, half * sizeof(int), st));
+    *counter = c.ring.p + slot;
+    return 0;
+}
 
 // One traversal launch: n queries at xq_d (device-addressable, 16-byte aligned rows of dp floats).
 // `overlap`: launch with programmatic stream serialisation, so that this launch's CTAs may start filling
@@ -905,10 +916,11 @@ int bh_index_reset(bh_index* h) {
 
 int bh_index_set_vector_storage(bh_index* h, int storage) {
     if (!h) return fail("null index");
-    if (storage != BH_STORAGE_F32 && storage != BH_STORAGE_F16) return fail("unknown storage kind");
+    if (storage != BH_STORAGE_F32 && storage != BH_STORAGE_F16 && storage != BH_STORAGE_BF16)
+        return fail("unknown storage kind");
     std::unique_lock<std::shared_mutex> lk(h->rw);
     if (h->ntotal != 0) return fail("set_vector_storage: the index is not empty");
-    if (storage != h->storage) {  // capacities are counted in rows of the old width: start over
+    if ((storage != BH_STORAGE_F32) != h->half()) {  // capacities are counted in rows of the old width: start over
         cudaSetDevice(h->device);
         cudaStreamSynchronize(h->stream);
         h->vecs.release();
@@ -971,11 +983,9 @@ int bh_index_search_device(const bh_index* h, int64_t n, const float* x, int64_t
     // query's latency the SMs are half empty (~13 % of a 10k-query step at efSearch=64). Launched with
     // programmatic stream serialisation, the next batch's CTAs take the freed slots at once. Every other
     // stream operation (copies, events, the caller's kernels, add()) still waits for all earlier launches.
-    const unsigned seq = c.ring_seq++;
-    const unsigned slot = seq % SearchCtx::kRing, half = SearchCtx::kRing / 2;
-    if (slot % half == 0)  // entering a half: zero the OTHER half (its launches are >= 32 calls old)
-        BH_CUDA(cudaMemsetAsync(c.ring.p + (slot == 0 ? half : 0), 0, half * sizeof(int), st));
-    return search_device_impl(h, st, c.ring.p + slot, n, x, k, distances, labels, params ? params->stats : nullptr,
+    int* counter = nullptr;
+    if (int rc = next_ring_counter(c, st, &counter)) return rc;
+    return search_device_impl(h, st, counter, n, x, k, distances, labels, params ? params->stats : nullptr,
                               params, params ? params->sel_bitmap : nullptr, 0, nullptr, true);
 }
 
@@ -1125,7 +1135,7 @@ int bh_index_reconstruct_n(const bh_index* h, int64_t i0, int64_t ni, float* out
         const char* src = reinterpret_cast<const char*>(h->vecs.p);
         for (int64_t j0 = 0; j0 < ni; j0 += chunk) {
             const int64_t m = std::min(chunk, ni - j0);
-            BH_CUDA(bh::launch_f16_to_f32(src + (size_t)(i0 + j0) * dp * 2, h->conv_d.p, (size_t)m * dp, nullptr));
+            BH_CUDA(bh::launch_f16_to_f32(src + (size_t)(i0 + j0) * dp * 2, h->conv_d.p, (size_t)m * dp, nullptr, h->fmt16()));
             BH_CUDA(cudaMemcpy2D(out + (size_t)j0 * d, (size_t)d * sizeof(float), h->conv_d.p, (size_t)dp * sizeof(float),
                                  (size_t)d * sizeof(float), (size_t)m, cudaMemcpyDeviceToHost));
         }
@@ -1314,8 +1324,8 @@ struct bh_shards {
     bh_index* local = nullptr;
     int rank = 0, nranks = 1;
     int64_t max_q = 0, max_k = 0;
-    unsigned long long* arena = nullptr;  // [2 parities][nranks][max_q * max_k] packed keys, then the flags
-    size_t parity_elems = 0;              // nranks * max_q * max_k
+    unsigned long long* arena = nullptr;  // [kShardRing][nranks][max_q * max_k] packed keys, then the flags
+    size_t parity_elems = 0;              // nranks * max_q * max_k (one ring slot)
     unsigned long long* flags = nullptr;  // [nranks * kFlagStride], slot r = last epoch rank r published
     unsigned long long* peer_arena[bh::kMaxPeers] = {};
     bool peer_ipc[bh::kMaxPeers] = {};
@@ -1325,8 +1335,14 @@ struct bh_shards {
     int* status = nullptr;      // mapped host word: 1 = a peer did not publish within the timeout
     int* status_dev = nullptr;
     int timeout_ms = 20000;
+    // pipelined mode: flag + merge kernels run on `xstream`, so consecutive traversal launches stay adjacent on
+    // the index's stream and overlap their drain phases; evE[e % ring] = traversal e done, evF = merge e done
+    int pipelined = 0;
+    cudaStream_t xstream = nullptr;
+    cudaEvent_t evE[8] = {}, evF[8] = {};
     std::mutex mu;
 };
+constexpr int kShardRing = 8;  // gather-buffer ring: call e uses slot e % 8 on every rank
 
 namespace {
 struct ShardBlob {  // BH_SHARDS_BLOB_BYTES
@@ -1343,7 +1359,7 @@ constexpr uint32_t kBlobMagic = 0x62685348u;
 unsigned long long* gather_slot(unsigned long long* arena, size_t parity_elems, int parity, int src_rank,
                                 int64_t n, int64_t k) {
     // lists of one call are packed [src_rank][n][k] at the front of the parity's half
-    return arena + (size_t)parity * parity_elems + (size_t)src_rank * n * k;
+    return arena + (size_t)parity * parity_elems + (size_t)src_rank * n * k;  // parity = ring slot
 }
 }  // namespace
 
@@ -1365,10 +1381,15 @@ int bh_shards_create(bh_shards** out, bh_index* local, int rank, int nranks, int
     s->max_k = max_k;
     s->parity_elems = (size_t)nranks * max_queries * max_k;
     const size_t flag_elems = (size_t)nranks * bh::kFlagStride;
-    const size_t bytes = (2 * s->parity_elems + flag_elems) * sizeof(unsigned long long);
+    const size_t bytes = (kShardRing * s->parity_elems + flag_elems) * sizeof(unsigned long long);
     BH_CUDA(cudaMalloc((void**)&s->arena, bytes));  // plain cudaMalloc: exportable with cudaIpcGetMemHandle
-    s->flags = s->arena + 2 * s->parity_elems;
+    s->flags = s->arena + kShardRing * s->parity_elems;
     cudaError_t e = cudaMemset(s->arena, 0, bytes);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->xstream, cudaStreamNonBlocking);
+    for (int i = 0; i < kShardRing && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&s->evE[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->evF[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->status, sizeof(int), cudaHostAllocMapped);
     if (e == cudaSuccess) {
         *s->status = 0;
@@ -1377,6 +1398,11 @@ int bh_shards_create(bh_shards** out, bh_index* local, int rank, int nranks, int
     if (e != cudaSuccess) {
         cudaFree(s->arena);
         if (s->status) cudaFreeHost(s->status);
+        if (s->xstream) cudaStreamDestroy(s->xstream);
+        for (int i = 0; i < kShardRing; i++) {
+            if (s->evE[i]) cudaEventDestroy(s->evE[i]);
+            if (s->evF[i]) cudaEventDestroy(s->evF[i]);
+        }
         return fail(std::string("shards_create: ") + cudaGetErrorString(e));
     }
     s->peer_arena[rank] = s->arena;
@@ -1390,6 +1416,14 @@ int bh_shards_free(bh_shards* s) {
     if (!s) return 0;
     cudaSetDevice(s->local->device);
     cudaStreamSynchronize(s->local->stream);
+    if (s->xstream) {
+        cudaStreamSynchronize(s->xstream);
+        cudaStreamDestroy(s->xstream);
+    }
+    for (int i = 0; i < kShardRing; i++) {
+        if (s->evE[i]) cudaEventDestroy(s->evE[i]);
+        if (s->evF[i]) cudaEventDestroy(s->evF[i]);
+    }
     for (int p = 0; p < s->nranks; p++)
         if (s->peer_ipc[p] && s->peer_arena[p]) cudaIpcCloseMemHandle(s->peer_arena[p]);
     if (s->arena) cudaFree(s->arena);
@@ -1476,7 +1510,13 @@ int bh_shards_post(bh_shards* s, int64_t n, const float* x, int64_t k, const bh_
     SearchCtx& c = *lease.c;
     cudaStream_t st = c.lane[0].stream;
     s->epoch++;
-    const int parity = (int)(s->epoch & 1);
+    const int parity = (int)(s->epoch % kShardRing);
+    const bool piped = s->pipelined && publish_to_peers;
+    // Pipelined flow control: rank A's call e stores into slot e % 8 of every peer, which that peer's merge
+    // e-8 must have finished reading. Every fourth call this stream waits for its OWN merge of four calls
+    // earlier: that merge needed every rank's flag e'-4, each raised (in order, on that rank's exchange
+    // stream) after the rank's merge e'-5 — so all merges up to e'-5 >= e-8 are done for the next four calls.
+    if (piped && s->epoch % 4 == 0 && s->epoch >= 8) BH_CUDA(cudaStreamWaitEvent(st, s->evF[(s->epoch - 4) % kShardRing], 0));
     unsigned long long* outs[bh::kMaxPeers];
     int n_out = 0;
     if (publish_to_peers) {
@@ -1493,14 +1533,23 @@ int bh_shards_post(bh_shards* s, int64_t n, const float* x, int64_t k, const bh_
             BH_CUDA(copy_rows_padded_async(c.q_d.p, x, n, h->d, h->dp, cudaMemcpyDeviceToDevice, st));
             x = c.q_d.p;
         }
-        if (int rc = search_device_impl(h, st, c.counters.p, n, x, k, nullptr, nullptr, nullptr, params, nullptr,
-                                        n_out, outs))
+        int* counter = c.counters.p;
+        if (piped)
+            if (int rc = next_ring_counter(c, st, &counter)) return rc;
+        if (int rc = search_device_impl(h, st, counter, n, x, k, nullptr, nullptr, nullptr, params, nullptr, n_out, outs,
+                                        piped))
             return rc;
+    }
+    cudaStream_t xs = st;
+    if (piped) {  // flag (and later the merge) on the exchange stream, behind this traversal only
+        BH_CUDA(cudaEventRecord(s->evE[parity], st));
+        BH_CUDA(cudaStreamWaitEvent(s->xstream, s->evE[parity], 0));
+        xs = s->xstream;
     }
     if (publish_to_peers && s->nranks > 1) {
         bh::PeerFlags pf{};
-        for (int p = 0; p < s->nranks; p++) pf.v[p] = s->peer_arena[p] + 2 * s->parity_elems;
-        BH_CUDA(bh::launch_shard_signal(s->nranks, s->rank, pf, s->epoch, st));
+        for (int p = 0; p < s->nranks; p++) pf.v[p] = s->peer_arena[p] + kShardRing * s->parity_elems;
+        BH_CUDA(bh::launch_shard_signal(s->nranks, s->rank, pf, s->epoch, xs));
     }
     return 0;
 }
@@ -1510,7 +1559,7 @@ int bh_shards_post(bh_shards* s, int64_t n, const float* x, int64_t k, const bh_
 // per rank) fills the other slices, then calls bh_shards_collect with wait_for_peers = 0
 int bh_shards_gather(bh_shards* s, int64_t n, int64_t k, void** ptr) {
     if (!s || !ptr) return fail("null argument");
-    *ptr = gather_slot(s->arena, s->parity_elems, (int)(s->epoch & 1), 0, n, k);
+    *ptr = gather_slot(s->arena, s->parity_elems, (int)(s->epoch % kShardRing), 0, n, k);
     return 0;
 }
 
@@ -1530,10 +1579,34 @@ int bh_shards_collect(bh_shards* s, int64_t n, int64_t k, float* distances, int6
         acc += s->ntotals[p];
     }
     const bool wait = wait_for_peers && s->nranks > 1;
+    const int slot = (int)(s->epoch % kShardRing);
+    const bool piped = s->pipelined && wait_for_peers;
     BH_CUDA(bh::launch_merge_packed(s->nranks, n, (int)k, h->metric == BH_METRIC_L2,
-                                    gather_slot(s->arena, s->parity_elems, (int)(s->epoch & 1), 0, n, k), off,
+                                    gather_slot(s->arena, s->parity_elems, slot, 0, n, k), off,
                                     distances, labels, wait ? s->flags : nullptr, s->epoch, s->status_dev,
-                                    s->timeout_ms, h->stream));
+                                    s->timeout_ms, piped ? s->xstream : h->stream));
+    if (piped) BH_CUDA(cudaEventRecord(s->evF[slot], s->xstream));
+    return 0;
+}
+
+// Pipelined mode (off by default): the flag and merge kernels of a search go to a separate exchange stream, so
+// the index's stream carries nothing but traversal launches, which then overlap their drain phases call after
+// call and no longer wait for slower peers' flags. D / I of a call are complete only after
+// bh_shards_join. Pass different D / I buffers to calls whose results you have not joined yet — or the same
+// ones if only the last call's results matter (merges run in call order). Join before switching the mode.
+int bh_shards_set_pipelined(bh_shards* s, int on) {
+    if (!s) return fail("null shards handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->pipelined = on ? 1 : 0;
+    return 0;
+}
+// make `stream` (cudaStream_t as void*; NULL = the local index's stream) wait for the most recent call's merge
+int bh_shards_join(bh_shards* s, void* stream) {
+    if (!s) return fail("null shards handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (!s->pipelined || s->epoch == 0) return 0;
+    BH_CUDA(cudaSetDevice(s->local->device));
+    BH_CUDA(cudaStreamWaitEvent(stream ? (cudaStream_t)stream : s->local->stream, s->evF[s->epoch % kShardRing], 0));
     return 0;
 }
 
@@ -1542,7 +1615,7 @@ int bh_shards_local_lists(bh_shards* s, int64_t n, int64_t k, float* distances, 
     if (!s || !distances || !labels) return fail("null argument");
     const bh_index* h = s->local;
     BH_CUDA(cudaSetDevice(h->device));
-    BH_CUDA(bh::launch_unpack(gather_slot(s->arena, s->parity_elems, (int)(s->epoch & 1), s->rank, n, k), n * k,
+    BH_CUDA(bh::launch_unpack(gather_slot(s->arena, s->parity_elems, (int)(s->epoch % kShardRing), s->rank, n, k), n * k,
                               h->metric == BH_METRIC_L2, distances, labels, h->stream));
     return 0;
 }

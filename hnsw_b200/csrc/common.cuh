@@ -17,7 +17,7 @@ constexpr int kVisitedAssoc16 = 1;  // 8-way buckets of 16-bit quotients, FIFO e
 constexpr int kVisitedAssoc32 = 2;  // 4-way buckets of 32-bit ids, FIFO eviction
 
 // Device-side view of one index shard (SURVEY §8a1/a2 re-laid-out for HBM):
-//   vecs       [ntotal][d] row-major (faiss IndexFlat codes): fp32, or IEEE fp16 when `half` is set
+//   vecs       [ntotal][d] row-major (faiss IndexFlat codes): fp32, or fp16 / bf16 when `half` is set
 //              (opt-in storage mode). Either way a row is `nchunk` 16-byte chunks, so row addressing
 //              is the same; only a chunk's interpretation differs (4 floats vs 8 halfs).
 //   nbr0       int32 [ntotal][deg0]   level-0 rows, deg0 = 2M, -1 terminated
@@ -30,7 +30,7 @@ struct GraphView {
     int32_t* upper_nbr;
     int d;
     int nchunk;  // 16-byte chunks per stored row: d / 4 (fp32) or d / 8 (fp16)
-    int half;    // 1 = fp16 storage
+    int half;    // 16-bit storage: 1 = IEEE fp16, 2 = bfloat16 (0 = fp32)
     int deg0;
     int degU;
     int entry_point;
@@ -63,17 +63,26 @@ __device__ __forceinline__ uint32_t hash_id(uint32_t id, int bits) {
 }
 
 // ---- stored chunk -> fp32 --------------------------------------------------------------
-// ES = float4s per 16-byte stored chunk (1: fp32 storage, 2: fp16 storage, exact widening).
+// ES = float4s per 16-byte stored chunk (1: fp32 storage, 2: 16-bit storage, exact widening).
+// fmt (16-bit storage only; uniform per index): 1 = IEEE fp16, 2 = bfloat16 (GraphView::half).
 template <bool HALF>
-__device__ __forceinline__ void chunk_to_f32(const float4& raw, float4 (&out)[HALF ? 2 : 1]) {
+__device__ __forceinline__ void chunk_to_f32(const float4& raw, float4 (&out)[HALF ? 2 : 1], int fmt = 1) {
     if constexpr (!HALF) {
         out[0] = raw;
     } else {
-        const __half2* h = reinterpret_cast<const __half2*>(&raw);
-        const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
-        const float2 c = __half22float2(h[2]), d = __half22float2(h[3]);
-        out[0] = make_float4(a.x, a.y, b.x, b.y);
-        out[1] = make_float4(c.x, c.y, d.x, d.y);
+        if (fmt == 2) {  // bf16 -> fp32 is the top half of the fp32 pattern
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw);
+            out[0] = make_float4(__uint_as_float(w[0] << 16), __uint_as_float(w[0] & 0xFFFF0000u),
+                                 __uint_as_float(w[1] << 16), __uint_as_float(w[1] & 0xFFFF0000u));
+            out[1] = make_float4(__uint_as_float(w[2] << 16), __uint_as_float(w[2] & 0xFFFF0000u),
+                                 __uint_as_float(w[3] << 16), __uint_as_float(w[3] & 0xFFFF0000u));
+        } else {
+            const __half2* h = reinterpret_cast<const __half2*>(&raw);
+            const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+            const float2 c = __half22float2(h[2]), d = __half22float2(h[3]);
+            out[0] = make_float4(a.x, a.y, b.x, b.y);
+            out[1] = make_float4(c.x, c.y, d.x, d.y);
+        }
     }
 }
 // acc += sum over the 4 lanes of (a-b)^2 (L2) or a*b (IP), one fmaf chain, fixed order x,y,z,w.

@@ -99,9 +99,10 @@ cudaError_t launch_merge_packed(int nshard, int64_t nq, int k, int is_l2, const 
 cudaError_t launch_unpack(const unsigned long long* keys, int64_t n, int is_l2, float* D, int64_t* I,
                           cudaStream_t stream);
 
-// ---- storage conversion (merge_kernel.cu): fp32 rows <-> fp16 rows, element-wise RNE / exact widening
-cudaError_t launch_f32_to_f16(const float* src, void* dst, size_t n, cudaStream_t stream);
-cudaError_t launch_f16_to_f32(const void* src, float* dst, size_t n, cudaStream_t stream);
+// ---- storage conversion (merge_kernel.cu): fp32 rows <-> 16-bit rows (fmt 1 = IEEE fp16, 2 = bfloat16),
+//      element-wise round-to-nearest-even / exact widening
+cudaError_t launch_f32_to_f16(const float* src, void* dst, size_t n, cudaStream_t stream, int fmt = 1);
+cudaError_t launch_f16_to_f32(const void* src, float* dst, size_t n, cudaStream_t stream, int fmt = 1);
 
 void count_launch(int n = 1);
 

@@ -159,6 +159,22 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restr
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         dst[i] = __float2half_rn(src[i]);
 }
+// fp32 -> bfloat16, round to nearest even (NaN kept quiet); bfloat16 -> fp32 is exact
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t u = __float_as_uint(src[i]);
+        uint16_t r;
+        if ((u & 0x7FFFFFFFu) > 0x7F800000u)
+            r = (uint16_t)((u >> 16) | 0x0040u);
+        else
+            r = (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+        dst[i] = r;
+    }
+}
+__global__ void bf16_to_f32_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = __uint_as_float((uint32_t)src[i] << 16);
+}
 __global__ void f16_to_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         dst[i] = __half2float(src[i]);
@@ -166,17 +182,23 @@ __global__ void f16_to_f32_kernel(const __half* __restrict__ src, float* __restr
 
 }  // namespace
 
-cudaError_t launch_f32_to_f16(const float* src, void* dst, size_t n, cudaStream_t stream) {
+cudaError_t launch_f32_to_f16(const float* src, void* dst, size_t n, cudaStream_t stream, int fmt) {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 32);
-    f32_to_f16_kernel<<<grid, 256, 0, stream>>>(src, static_cast<__half*>(dst), n);
+    if (fmt == 2)
+        f32_to_bf16_kernel<<<grid, 256, 0, stream>>>(src, static_cast<uint16_t*>(dst), n);
+    else
+        f32_to_f16_kernel<<<grid, 256, 0, stream>>>(src, static_cast<__half*>(dst), n);
     count_launch();
     return cudaGetLastError();
 }
-cudaError_t launch_f16_to_f32(const void* src, float* dst, size_t n, cudaStream_t stream) {
+cudaError_t launch_f16_to_f32(const void* src, float* dst, size_t n, cudaStream_t stream, int fmt) {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 32);
-    f16_to_f32_kernel<<<grid, 256, 0, stream>>>(static_cast<const __half*>(src), dst, n);
+    if (fmt == 2)
+        bf16_to_f32_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(src), dst, n);
+    else
+        f16_to_f32_kernel<<<grid, 256, 0, stream>>>(static_cast<const __half*>(src), dst, n);
     count_launch();
     return cudaGetLastError();
 }

@@ -63,21 +63,23 @@ class _HNSWFields:
 
 STORAGE_F32 = 0
 STORAGE_F16 = 1
+STORAGE_BF16 = 2
 
 
 class IndexHNSWFlat:
     def __init__(self, d: int, M: int = 32, metric: int = METRIC_L2, device: int = 0,
                  storage: str | int = "fp32"):
-        """`storage="fp16"` (opt-in, not faiss-bit-comparable): rows are kept as IEEE fp16 in HBM and
+        """`storage="fp16"` / `"bf16"` (opt-in, not faiss-bit-comparable): rows are kept in 16 bits in HBM and
         accumulated in fp32 — half the gather bytes; the API stays fp32."""
         L = _lib.lib()
         h = C.c_void_p()
         _lib.check(L.bh_index_create(C.byref(h), int(d), int(M), int(metric), int(device)))
         self._h = h
-        kind = {"fp32": STORAGE_F32, "f32": STORAGE_F32, "fp16": STORAGE_F16, "f16": STORAGE_F16}.get(storage, storage)
+        kind = {"fp32": STORAGE_F32, "f32": STORAGE_F32, "fp16": STORAGE_F16, "f16": STORAGE_F16,
+                "bf16": STORAGE_BF16, "bfloat16": STORAGE_BF16}.get(storage, storage)
         if kind != STORAGE_F32:
             _lib.check(L.bh_index_set_vector_storage(h, int(kind)))
-        self.storage = "fp16" if kind == STORAGE_F16 else "fp32"
+        self.storage = {STORAGE_F16: "fp16", STORAGE_BF16: "bf16"}.get(kind, "fp32")
         self.d = int(d)
         self.M = int(M)
         self.metric_type = int(metric)

@@ -123,6 +123,32 @@ class ShardedIndexHNSWFlat:
         self.exchange_kind = kind
         _lib.check(L.bh_shards_set_ntotals(s, self.ntotals.ctypes.data))
 
+    # ---- pipelined serving loop (GPU path): enqueue batch after batch, join when results are needed
+    def set_pipelined(self, on: bool):
+        """On: flag + merge kernels run on the engine's exchange stream, so back-to-back `enqueue` calls keep the
+        index's stream full of traversal launches (they overlap their drain phases and do not wait for slower
+        peers). Results of a call are complete only after `join()`."""
+        from . import _lib
+        if not self._s:
+            raise RuntimeError("call search() once first (it creates and connects the exchange buffers)")
+        _lib.check(_lib.lib().bh_shards_set_pipelined(self._s, int(bool(on))))
+
+    def enqueue(self, q_dev, k: int, D_out, I_out, efSearch: int | None = None):
+        """Collective. q_dev: float32 [nq, d] CUDA tensor already present (and complete) on every rank; D_out / I_out:
+        float32 / int64 [nq, k] CUDA tensors. Enqueues on the index's stream; nothing is synchronised."""
+        from . import _lib
+        from ._lib import SearchParams
+        p = SearchParams(int(efSearch or 0), 0, 0, 0, None, None, 0, 0, 0)
+        _lib.check(_lib.lib().bh_shards_search_device(self._s, int(q_dev.shape[0]), q_dev.data_ptr(), int(k),
+                                                      D_out.data_ptr(), I_out.data_ptr(), C.byref(p)))
+
+    def join(self, stream=None):
+        """Make `stream` (a torch stream; default: the current one) wait for the latest enqueued call's results."""
+        import torch
+        from . import _lib
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        _lib.check(_lib.lib().bh_shards_join(self._s, st.cuda_stream))
+
     def search(self, xq, k: int, efSearch: int | None = None, src: int = 0, keep_local: bool = False):
         """xq: [nq, d] float32 on rank `src` (other ranks pass an array of the same shape).
         Returns (D, I) with global ids on every rank (device tensors on the GPU path).

@@ -65,7 +65,9 @@ typedef struct bh_build_params {
 /* vector storage inside the index (the API is fp32 either way) */
 #define BH_STORAGE_F32 0 /* faiss IndexFlat codes: the default, bit-comparable to faiss */
 #define BH_STORAGE_F16 1 /* opt-in: rows rounded to IEEE fp16 on add, fp32 accumulation; halves the gather
-                            bytes; distances differ from fp32 storage by ~1e-3 relative; needs d % 8 == 0 */
+                            bytes; distances differ from fp32 storage by ~1e-3 relative */
+#define BH_STORAGE_BF16 2 /* opt-in: rows rounded to bfloat16 on add (fp32's range, 8 bits of mantissa: ~4e-3
+                             relative per component), fp32 accumulation */
 
 /* -- lifecycle ------------------------------------------------------------------- */
 /* replaces faiss::IndexHNSWFlat::IndexHNSWFlat(int d, int M, MetricType metric) */
@@ -193,6 +195,13 @@ int bh_shards_gather(bh_shards* s, int64_t n, int64_t k, void** ptr);
 int bh_shards_collect(bh_shards* s, int64_t n, int64_t k, float* distances, int64_t* labels,
                       int wait_for_peers);
 int bh_shards_local_lists(bh_shards* s, int64_t n, int64_t k, float* distances, int64_t* labels);
+/* Pipelined mode (off by default). On: the flag and merge kernels run on a separate exchange stream, so the
+ * index's stream carries only traversal launches — consecutive calls overlap their drain phases and do not
+ * wait for slower peers; D / I of a call are complete only after bh_shards_join(s, stream) has made `stream`
+ * (cudaStream_t as void*, NULL = the local index's stream) wait for the latest merge. Merges run in call
+ * order. Join before switching the mode back. */
+int bh_shards_set_pipelined(bh_shards* s, int on);
+int bh_shards_join(bh_shards* s, void* stream);
 /* 0 = fine; 1 = a peer did not publish within the timeout (results of that call are undefined) */
 int bh_shards_status(bh_shards* s);
 

@@ -141,6 +141,18 @@ inline float round_to_half(float f) {
     return out;
 }
 
+// Round to bfloat16 (round-to-nearest-even) and back, like the engine's f32_to_bf16_kernel.
+inline float round_to_bf16(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    if ((u & 0x7FFFFFFFu) > 0x7F800000u)
+        u = (u | 0x00400000u) & 0xFFFF0000u;
+    else
+        u = (u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
 struct Oracle;
 
 // DistanceComputer (A.3): query↔stored and stored↔stored; IP is negated so that
@@ -276,7 +288,7 @@ struct Oracle {
     int efConstruction = 40, efSearch = 16;  // A.1 defaults
     bool check_relative_distance = true;
     int team = 0;
-    bool half_storage = false;  // vectors rounded to IEEE fp16 on add (the engine's opt-in storage mode)
+    int half_storage = 0;  // 1: vectors rounded to IEEE fp16 on add, 2: to bfloat16 (the engine's opt-in storage modes)
     std::vector<double> assign_probas;
     std::vector<int> cum_nneighbor_per_level;
     std::vector<int> levels;      // level+1 per vertex
@@ -678,7 +690,7 @@ int orc_set_team(void* p, int T) {
 int orc_set_half_storage(void* p, int on) {
     Oracle* o = static_cast<Oracle*>(p);
     if (o->ntotal != 0 || (on && o->d % 8 != 0)) return 1;
-    o->half_storage = on != 0;
+    o->half_storage = on;  // 0 off, 1 fp16, 2 bf16
     return 0;
 }
 float orc_round_to_half(float f) { return round_to_half(f); }
@@ -705,7 +717,8 @@ int orc_add(void* p, int64_t n, const float* x, int nthreads, int32_t* order_out
     size_t n0 = (size_t)o->ntotal;
     o->xb.insert(o->xb.end(), x, x + (size_t)n * o->d);
     if (o->half_storage)
-        for (size_t i = n0 * o->d; i < o->xb.size(); i++) o->xb[i] = round_to_half(o->xb[i]);
+        for (size_t i = n0 * o->d; i < o->xb.size(); i++)
+            o->xb[i] = o->half_storage == 2 ? round_to_bf16(o->xb[i]) : round_to_half(o->xb[i]);
     o->ntotal += n;
     // The build reads vectors from o->xb (which may have been reallocated), so pass
     // the stored copy, not the caller's pointer.
@@ -799,7 +812,7 @@ int orc_import(void* p, int64_t n, const float* x, const int* levels, const int3
     Oracle* o = static_cast<Oracle*>(p);
     o->xb.assign(x, x + (size_t)n * o->d);
     if (o->half_storage)
-        for (float& v : o->xb) v = round_to_half(v);
+        for (float& v : o->xb) v = o->half_storage == 2 ? round_to_bf16(v) : round_to_half(v);
     o->ntotal = n;
     o->levels.assign(levels, levels + n);
     o->offsets.assign(1, 0);

@@ -131,9 +131,11 @@ class OracleHNSWFlat:
         if self._L.orc_set_team(self._h, int(T)) != 0:
             raise ValueError("bad team")
 
-    def set_half_storage(self, on: bool = True):
-        """Emulate the engine's opt-in fp16 vector storage (vectors rounded to binary16 on add)."""
-        if self._L.orc_set_half_storage(self._h, int(bool(on))) != 0:
+    def set_half_storage(self, on=True):
+        """Emulate the engine's opt-in 16-bit vector storage: True / 1 / "fp16" = vectors rounded to binary16 on
+        add, 2 / "bf16" = to bfloat16."""
+        kind = {"fp16": 1, "bf16": 2}[on] if isinstance(on, str) else int(on)
+        if self._L.orc_set_half_storage(self._h, kind) != 0:
             raise ValueError("set_half_storage: index not empty or d % 8 != 0")
 
     def set_check_relative_distance(self, v: bool):

@@ -17,7 +17,7 @@ UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 out = {"kernel_src_sha": kernel_source_sha(), "how": "ncu --set full --clock-control none; dram__bytes_read.sum + "
        "dram__bytes_write.sum of ONE beam_kernel launch over the bench.py batch (scripts/profile_search.py --bench-data 1)",
        "entries": {}}
-path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+path = os.environ.get("TRAFFIC_JSON", os.path.join(ROOT, "profiles", "r2_traffic.json"))
 if os.path.exists(path):
     old = json.load(open(path))
     if old.get("kernel_src_sha") == out["kernel_src_sha"]:

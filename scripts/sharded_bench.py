@@ -101,7 +101,26 @@ for ef in [int(e) for e in a.efs.split(",")]:
     f1.record(st1); sh.local.synchronize()
     ms1p = torch.tensor([f0.elapsed_time(f1) / a.steps], device=dev)
     dist.all_reduce(ms1p, op=dist.ReduceOp.MAX)
-    rows.append({"efSearch": ef, "ms_per_batch": round(float(ms.item()), 3), "qps": round(a.nq / float(ms.item()) * 1e3),
+    # pipelined serving loop (bh_shards_set_pipelined): enqueue back to back, join once
+    Dp = torch.empty(a.nq, a.k, device=dev); Ip = torch.empty(a.nq, a.k, dtype=torch.int64, device=dev)
+    sh.set_pipelined(True)
+    for _ in range(3):
+        sh.enqueue(xq, a.k, Dp, Ip, efSearch=ef)
+    sh.join(st1); sh.local.synchronize(); dist.barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(st1)
+    for _ in range(a.steps):
+        sh.enqueue(xq, a.k, Dp, Ip, efSearch=ef)
+    sh.join(st1); p1.record(st1); sh.local.synchronize()
+    msp = torch.tensor([p0.elapsed_time(p1) / a.steps], device=dev)
+    dist.all_reduce(msp, op=dist.ReduceOp.MAX)
+    same = bool(torch.equal(Ip, I)) and bool(torch.equal(Dp, D))
+    sh.set_pipelined(False)
+    dist.barrier()
+    rows.append({"pipelined_ms_per_batch": round(float(msp.item()), 3), "pipelined_qps": round(a.nq / float(msp.item()) * 1e3),
+                 "pipelined_equals_synchronous": same,
+                 "pipelined_efficiency_vs_pipelined_single_shard": round(float(ms1p.item()) / float(msp.item()), 4),
+                 "efSearch": ef, "ms_per_batch": round(float(ms.item()), 3), "qps": round(a.nq / float(ms.item()) * 1e3),
                  "recall_at_10": round(rec, 4), "ms_shard_alone_max_over_ranks": round(float(ms1.item()), 3),
                  "efficiency_vs_single_shard": round(float(ms1.item()) / float(ms.item()), 4),
                  "ms_shard_alone_pipelined": round(float(ms1p.item()), 3),

@@ -212,3 +212,46 @@ def test_rejected_add_leaves_index_untouched(oracle_mod):
     idx.add(xb)
     go, gg = o.export_graph(), idx.export_graph()
     assert np.array_equal(gg["levels"], go["levels"]) and np.array_equal(gg["neighbors"], go["neighbors"])
+
+
+def _round_bf16(x):
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+@pytest.mark.parametrize("d,M,team,metric", [(128, 16, 8, 1), (64, 8, 8, 0), (768, 8, 32, 0), (20, 8, 8, 1)])
+def test_bf16_storage_bit_exact_vs_oracle_bf16_mode(oracle_mod, d, M, team, metric):
+    """Opt-in bfloat16 vector storage (rows rounded to nearest-even bf16 on add, exact widening, fp32
+    accumulation in the kernels' fixed order): sequential build and search are bit-equal to the oracle's bf16
+    mode, reconstruct returns the rounded rows. d=20 also exercises zero-padding to whole 16-byte chunks."""
+    import hnsw_b200
+    n = 1200
+    dp = (d + 7) // 8 * 8
+    xb, xq = synthetic_dataset(d, n, 50, normalize=(metric == 0))
+    pad = lambda a: np.ascontiguousarray(np.pad(a, ((0, 0), (0, dp - d))))
+    o = oracle_mod.OracleHNSWFlat(dp, M, metric)
+    o.set_half_storage("bf16")
+    o.set_team(team)
+    o.efConstruction = 32
+    o.add(pad(xb))
+    idx = hnsw_b200.IndexHNSWFlat(d, M, metric, storage="bf16")
+    assert idx.storage == "bf16"
+    idx.hnsw.efConstruction = 32
+    idx.set_build_params(max_batch=1)
+    idx.add(xb)
+    go, gg = o.export_graph(), idx.export_graph()
+    assert np.array_equal(gg["levels"], go["levels"]) and np.array_equal(gg["neighbors"], go["neighbors"])
+    for ef in (16, 64):
+        Do, Io, So = o.search(pad(xq), 10, ef, stats=True)
+        D, I, S = idx.search(xq, 10, efSearch=ef, stats=True, hash_bits=13)
+        assert np.array_equal(I, Io) and np.array_equal(D, Do) and np.array_equal(S, So)
+        D, I = idx.search(xq, 10, efSearch=ef)                      # default visited table
+        assert np.array_equal(I, Io) and np.array_equal(D, Do)
+    assert np.array_equal(idx.reconstruct_n(0, 40), _round_bf16(xb[:40]))
+    _, gt = oracle_mod.brute_force_knn(xb, xq, 10, metric)
+    assert oracle_mod.recall_at_k(idx.search(xq, 10, efSearch=128)[1], gt) > 0.85
+    b = hnsw_b200.IndexHNSWFlat(d, M, metric, storage="bf16")       # batched build: invariants hold
+    b.hnsw.efConstruction = 32
+    b.add(xb)
+    assert_graph_invariants(b.export_graph(), M, n)

@@ -453,6 +453,27 @@ def test_shards_cabi_two_ranks_emulated_on_one_gpu(metric):
                 outs.append((D.cpu().numpy(), I.cpu().numpy()))
             for D, I in outs:
                 assert np.array_equal(I, Iw) and np.array_equal(D, Dw)
+        # pipelined mode: flag + merge kernels on the exchange stream, results complete after join. (Still no
+        # kernel waits on a kernel here: everything queued is drained before the merges are launched.)
+        for r in range(2):
+            _lib.check(L.bh_shards_set_pipelined(hs[r], 1))
+        for rep in range(10):                      # > ring depth: slots are reused, flow-control waits are taken
+            for r in range(2):
+                _lib.check(L.bh_shards_post(hs[r], nq, q.data_ptr(), k, C.byref(p), 1))
+            torch.cuda.synchronize()
+            outs = []
+            for r in range(2):
+                D = torch.empty(nq, k, device="cuda")
+                I = torch.empty(nq, k, dtype=torch.int64, device="cuda")
+                _lib.check(L.bh_shards_collect(hs[r], nq, k, D.data_ptr(), I.data_ptr(), 1))
+                outs.append((D, I))
+            for r in range(2):
+                _lib.check(L.bh_shards_join(hs[r], None))
+                idxs[r].synchronize()
+                assert L.bh_shards_status(hs[r]) == 0
+                assert np.array_equal(outs[r][1].cpu().numpy(), Iw) and np.array_equal(outs[r][0].cpu().numpy(), Dw)
+        for r in range(2):
+            _lib.check(L.bh_shards_set_pipelined(hs[r], 0))
         # the caller exchanges the lists itself (what the NCCL fallback does with one all-gather)
         for r in range(2):
             _lib.check(L.bh_shards_post(hs[r], nq, q.data_ptr(), k, C.byref(p), 0))
