@@ -1339,10 +1339,10 @@ struct bh_shards {
     // the index's stream and overlap their drain phases; evE[e % ring] = traversal e done, evF = merge e done
     int pipelined = 0;
     cudaStream_t xstream = nullptr;
-    cudaEvent_t evE[8] = {}, evF[8] = {};
+    cudaEvent_t evE[16] = {}, evF[16] = {};
     std::mutex mu;
 };
-constexpr int kShardRing = 8;  // gather-buffer ring: call e uses slot e % 8 on every rank
+constexpr int kShardRing = 16;  // gather-buffer ring: call e uses slot e % 16 on every rank
 
 namespace {
 struct ShardBlob {  // BH_SHARDS_BLOB_BYTES
@@ -1512,11 +1512,14 @@ int bh_shards_post(bh_shards* s, int64_t n, const float* x, int64_t k, const bh_
     s->epoch++;
     const int parity = (int)(s->epoch % kShardRing);
     const bool piped = s->pipelined && publish_to_peers;
-    // Pipelined flow control: rank A's call e stores into slot e % 8 of every peer, which that peer's merge
-    // e-8 must have finished reading. Every fourth call this stream waits for its OWN merge of four calls
-    // earlier: that merge needed every rank's flag e'-4, each raised (in order, on that rank's exchange
-    // stream) after the rank's merge e'-5 — so all merges up to e'-5 >= e-8 are done for the next four calls.
-    if (piped && s->epoch % 4 == 0 && s->epoch >= 8) BH_CUDA(cudaStreamWaitEvent(st, s->evF[(s->epoch - 4) % kShardRing], 0));
+    // Pipelined flow control: rank A's call e stores into slot e % R of every peer, which that peer's merge
+    // e-R must have finished reading. Every R/2-th call this stream waits for its OWN merge of R/2 calls
+    // earlier (call e'): that merge needed every rank's flag e'-R/2, each raised (in order, on that rank's
+    // exchange stream) after the rank's merge e'-R/2-1 — so all merges up to e'-R/2-1 >= e-R are done for
+    // the calls e', ..., e'+R/2-1. (The wait breaks the launch adjacency once per R/2 calls.)
+    constexpr int kHalfRing = kShardRing / 2;
+    if (piped && s->epoch % kHalfRing == 0 && s->epoch >= (unsigned)kShardRing)
+        BH_CUDA(cudaStreamWaitEvent(st, s->evF[(s->epoch - kHalfRing) % kShardRing], 0));
     unsigned long long* outs[bh::kMaxPeers];
     int n_out = 0;
     if (publish_to_peers) {

@@ -71,11 +71,12 @@ __device__ __forceinline__ void chunk_to_f32(const float4& raw, float4 (&out)[HA
         out[0] = raw;
     } else {
         if (fmt == 2) {  // bf16 -> fp32 is the top half of the fp32 pattern
-            const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw);
-            out[0] = make_float4(__uint_as_float(w[0] << 16), __uint_as_float(w[0] & 0xFFFF0000u),
-                                 __uint_as_float(w[1] << 16), __uint_as_float(w[1] & 0xFFFF0000u));
-            out[1] = make_float4(__uint_as_float(w[2] << 16), __uint_as_float(w[2] & 0xFFFF0000u),
-                                 __uint_as_float(w[3] << 16), __uint_as_float(w[3] & 0xFFFF0000u));
+            const uint32_t w0 = __float_as_uint(raw.x), w1 = __float_as_uint(raw.y);
+            const uint32_t w2 = __float_as_uint(raw.z), w3 = __float_as_uint(raw.w);
+            out[0] = make_float4(__uint_as_float(w0 << 16), __uint_as_float(w0 & 0xFFFF0000u),
+                                 __uint_as_float(w1 << 16), __uint_as_float(w1 & 0xFFFF0000u));
+            out[1] = make_float4(__uint_as_float(w2 << 16), __uint_as_float(w2 & 0xFFFF0000u),
+                                 __uint_as_float(w3 << 16), __uint_as_float(w3 & 0xFFFF0000u));
         } else {
             const __half2* h = reinterpret_cast<const __half2*>(&raw);
             const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);

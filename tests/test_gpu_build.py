@@ -241,7 +241,22 @@ def test_bf16_storage_bit_exact_vs_oracle_bf16_mode(oracle_mod, d, M, team, metr
     idx.set_build_params(max_batch=1)
     idx.add(xb)
     go, gg = o.export_graph(), idx.export_graph()
-    assert np.array_equal(gg["levels"], go["levels"]) and np.array_equal(gg["neighbors"], go["neighbors"])
+    assert np.array_equal(gg["levels"], go["levels"])
+    # "identical except for distance ties" (BASELINE north_star): 8 mantissa bits make two neighbours at exactly
+    # the same distance from a vertex likelier; faiss's heap and the kernel's (distance, id) order may then list
+    # them in either order. Any differing slot must be such a swap: same neighbour SET in that row, both
+    # neighbours at the identical distance from the row's owner.
+    mism = np.flatnonzero(gg["neighbors"] != go["neighbors"])
+    assert mism.size <= 4, f"{mism.size} of {go['neighbors'].size} adjacency slots differ (first at {mism[:5]})"
+    if mism.size:
+        offs = go["offsets"].astype(np.int64)
+        xr = _round_bf16(pad(xb))
+        for v in np.unique(np.searchsorted(offs, mism, side="right") - 1):
+            a, b2 = gg["neighbors"][offs[v]:offs[v + 1]], go["neighbors"][offs[v]:offs[v + 1]]
+            assert np.array_equal(np.sort(a), np.sort(b2)), f"row of vertex {v}: different neighbour sets"
+            for sl in np.flatnonzero(a != b2):
+                assert o.distance(xr[v], xr[a[sl]]) == o.distance(xr[v], xr[b2[sl]]), "swap without a distance tie"
+        idx.import_graph(xb, go["levels"], go["neighbors"], go["entry_point"], go["max_level"])  # search the oracle's graph
     for ef in (16, 64):
         Do, Io, So = o.search(pad(xq), 10, ef, stats=True)
         D, I, S = idx.search(xq, 10, efSearch=ef, stats=True, hash_bits=13)
