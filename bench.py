@@ -42,11 +42,11 @@ L2_POLICY = "no flush: the index and the bytes touched per step both exceed the 
 CONFIGS = {
     "sift": dict(shape="SIFT1M-shape", n=1_000_000, d=128, d1=12, ip=False, M=32, efc=200, nq=10_000,
                  metric="QPS at recall@10>=0.95 (1M x128 L2)"),
-    "gist": dict(shape="GIST1M-shape", n=1_000_000, d=960, d1=12, ip=False, M=32, efc=200, nq=10_000,
+    "gist": dict(shape="GIST1M-shape", n=1_000_000, d=960, d1=16, ip=False, M=32, efc=200, nq=10_000,
                  metric="QPS at recall@10>=0.95 (1M x960 L2)"),
     "deep": dict(shape="Deep100M-shape shard (1/8 of 100M)", n=12_500_000, d=96, d1=12, ip=False, M=32, efc=200,
                  nq=10_000, metric="QPS at recall@10>=0.95 (12.5M x96 L2 shard)"),
-    "ip768": dict(shape="embedding-shape", n=1_000_000, d=768, d1=12, ip=True, M=32, efc=200, nq=10_000,
+    "ip768": dict(shape="embedding-shape", n=1_000_000, d=768, d1=16, ip=True, M=32, efc=200, nq=10_000,
                   metric="QPS at recall@10>=0.95 (1M x768 IP)"),
 }
 

@@ -457,7 +457,7 @@ def test_shards_cabi_two_ranks_emulated_on_one_gpu(metric):
         # kernel waits on a kernel here: everything queued is drained before the merges are launched.)
         for r in range(2):
             _lib.check(L.bh_shards_set_pipelined(hs[r], 1))
-        for rep in range(10):                      # > ring depth: slots are reused, flow-control waits are taken
+        for rep in range(20):                      # > ring depth: slots are reused, flow-control waits are taken
             for r in range(2):
                 _lib.check(L.bh_shards_post(hs[r], nq, q.data_ptr(), k, C.byref(p), 1))
             torch.cuda.synchronize()
