@@ -3,7 +3,7 @@
 
 namespace bh {
 cudaError_t launch_beam_f16(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
-                              cudaStream_t stream, int* grid_out) {
-    return launch_by_chunks<true>(g, t, W, variant, num_sms, stream, grid_out);
+                              cudaStream_t stream, int* grid_out, const BuildBatch* fuse) {
+    return launch_by_chunks<true>(g, t, W, variant, num_sms, stream, grid_out, fuse);
 }
 }  // namespace bh

@@ -9,6 +9,7 @@
 // items from an atomic counter until the batch is drained.
 #include "beam.cuh"
 #include "engine.h"
+#include "select.cuh"
 
 #include <cfloat>
 #include <climits>
@@ -17,8 +18,13 @@
 
 namespace bh {
 
-template <int TEAM, int CPL, int W, int R, int G, int MINB, bool HALF>
-__global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, BeamTask t) {
+// FUSE (construction only): the warp that finished an insertion search runs shrink_neighbor_list on the
+// candidate list it still holds in shared memory, writes the new vertex's row and stages the back-edges —
+// what select_and_link_coop_kernel does as a separate launch. Legal inside the round: no vertex of the graph
+// links to a point of the round before the back-link kernel runs, so the rows written here are never read by
+// the round's other searches; the heuristic is instruction-bound and hides under the other warps' gathers.
+template <int TEAM, int CPL, int W, int R, int G, int MINB, bool HALF, bool FUSE>
+__global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, BeamTask t, BuildBatch b) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // Nothing this grid reads is produced by the launch before it, so the next search launch on the stream
     // may begin as soon as SM slots free up (no-op unless that launch asked for programmatic serialisation).
@@ -80,16 +86,57 @@ __global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, Bea
             const int lsize = t.sel ? s.ctrl[2] : s.ctrl[1];
             const unsigned long long* L = t.sel ? s.rlist : s.list;
             if (t.items) {
-                unsigned long long* out = t.out_lists + (size_t)wi * t.ef;
-                for (int i = lane; i < lsize; i += 32) out[i] = key_clean(L[i]);
-                if (lane == 0) {
-                    t.out_counts[wi] = lsize;
-                    if (t.build_counters) {  // totals for the build's roofline (bench.py)
-                        atomicAdd(t.build_counters + 0, (unsigned long long)st.ndis0);
-                        atomicAdd(t.build_counters + 1, (unsigned long long)st.nhops0);
-                        atomicAdd(t.build_counters + 2, (unsigned long long)st.ndis_up);
-                        atomicAdd(t.build_counters + 3, (unsigned long long)st.nhops_up);
+                if (t.build_counters && lane == 0) {  // totals for the build's roofline (bench.py)
+                    atomicAdd(t.build_counters + 0, (unsigned long long)st.ndis0);
+                    atomicAdd(t.build_counters + 1, (unsigned long long)st.nhops0);
+                    atomicAdd(t.build_counters + 2, (unsigned long long)st.ndis_up);
+                    atomicAdd(t.build_counters + 3, (unsigned long long)st.nhops_up);
+                }
+                if constexpr (FUSE) {
+                    const int4 it = __ldg(t.items + wi);
+                    const int pt = it.x;
+                    int deg;
+                    int32_t* row = row_ptr_rw(g, pt, level, deg);
+                    unsigned long long* Lw = s.list;
+                    for (int i = lane; i < lsize; i += 32) Lw[i] = key_clean(Lw[i]);
+                    __syncwarp();
+                    int K = lsize;
+                    const unsigned long long* kept = Lw;
+                    const bool verified = lsize >= deg;
+                    if (verified) {  // (fewer candidates than slots: shrink_neighbor_list keeps everything)
+                        K = heuristic<TEAM, CPL, false, HALF>(g, Lw, lsize, deg, s.cand_key, nullptr, nullptr, nullptr,
+                                                              nullptr, lane);
+                        kept = s.cand_key;
                     }
+                    __syncwarp();
+                    if (lane == 0) {
+                        *nver_ptr(g, b, pt, level) = verified ? (uint8_t)K : (uint8_t)0;
+                        if (t.build_counters && verified) atomicAdd(t.build_counters + 4, (unsigned long long)lsize);
+                    }
+                    // faiss pops link_targets farthest-first: row[i] = kept[K-1-i]
+                    for (int i = lane; i < g.deg0; i += 32) {
+                        const int e = wi * g.deg0 + i;
+                        if (i < K) {
+                            const unsigned long long key = kept[K - 1 - i];
+                            const int o = (int)key_id(key);
+                            row[i] = o;
+                            const int slot = row_slot(g, b.n_level0, o, level);
+                            b.edge_src[e] = pt;
+                            b.edge_dst[e] = o;
+                            b.edge_level[e] = level;
+                            b.edge_dist[e] = key_dist(key);
+                            b.edge_dst_slot[e] = slot;
+                            b.edge_next[e] = atomicExch(b.slot_head + slot, e);
+                        } else {
+                            if (i < deg) row[i] = -1;
+                            b.edge_dst_slot[e] = -1;
+                        }
+                    }
+                    __syncwarp();
+                } else {
+                    unsigned long long* out = t.out_lists + (size_t)wi * t.ef;
+                    for (int i = lane; i < lsize; i += 32) out[i] = key_clean(L[i]);
+                    if (lane == 0) t.out_counts[wi] = lsize;
                 }
             } else if (t.n_shard_out > 0) {
                 // sharded search: this shard's list goes straight into every rank's gather buffer (peer
@@ -98,6 +145,9 @@ __global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, Bea
                     const unsigned long long kk = i < lsize ? key_clean(L[i]) : ~0ull;
                     for (int p = 0; p < t.n_shard_out; p++) t.shard_out[p][(size_t)wi * t.k + i] = kk;
                 }
+                // the writer itself makes its peer stores visible system-wide; the flag that announces them is
+                // raised by a later kernel (release) and read with acquire by the peers' merge kernels
+                if (t.n_shard_out > 1) __threadfence_system();
             } else {
                 const float pad = g.is_l2 ? FLT_MAX : -FLT_MAX;
                 for (int i = lane; i < t.k; i += 32) {
@@ -131,10 +181,10 @@ __global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, Bea
 // ---------------------------------------------------------------- host dispatch
 namespace {
 
-template <int TEAM, int CPL, int W, int R, int G, int MINB, bool HALF>
-cudaError_t launch_one(const GraphView& g, const BeamTask& t, int num_sms, cudaStream_t stream,
-                       int* grid_out) {
-    auto kern = beam_kernel<TEAM, CPL, W, R, G, MINB, HALF>;
+template <int TEAM, int CPL, int W, int R, int G, int MINB, bool HALF, bool FUSE>
+cudaError_t launch_one_t(const GraphView& g, const BeamTask& t, int num_sms, cudaStream_t stream,
+                         int* grid_out, const BuildBatch& b) {
+    auto kern = beam_kernel<TEAM, CPL, W, R, G, MINB, HALF, FUSE>;
     const size_t smem = (size_t)G * group_smem_bytes(g.d, t.ef, 1 << t.hash_bits, g.deg0, t.sel ? t.k : 0);
     // the dynamic-shared-memory limit is an attribute of the FUNCTION: concurrent searches with different
     // efSearch would race between setting it and launching, so the pair is one critical section
@@ -162,10 +212,23 @@ cudaError_t launch_one(const GraphView& g, const BeamTask& t, int num_sms, cudaS
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, kern, g, t);
+        return cudaLaunchKernelEx(&cfg, kern, g, t, b);
     }
-    kern<<<(unsigned)grid, 32 * W * G, smem, stream>>>(g, t);
+    kern<<<(unsigned)grid, 32 * W * G, smem, stream>>>(g, t, b);
     return cudaGetLastError();
+}
+
+template <int TEAM, int CPL, int W, int R, int G, int MINB, bool HALF>
+cudaError_t launch_one(const GraphView& g, const BeamTask& t, int num_sms, cudaStream_t stream,
+                       int* grid_out, const BuildBatch* fuse) {
+    // The fused selection is instantiated for wide rows only (TEAM >= 16, i.e. rows above 512 B): measured at
+    // 300k x 768 it makes the build 9 % faster (the selection of a 3 KB-row item is long enough to be worth
+    // hiding under the gathers), at 1M x 128 it makes it 7 % slower (registers, longer drain of every round).
+    if constexpr (TEAM >= 16) {
+        if (fuse) return launch_one_t<TEAM, CPL, W, R, G, MINB, HALF, true>(g, t, num_sms, stream, grid_out, *fuse);
+    }
+    if (fuse) return cudaErrorInvalidValue;
+    return launch_one_t<TEAM, CPL, W, R, G, MINB, HALF, false>(g, t, num_sms, stream, grid_out, BuildBatch{});
 }
 
 // variant (W == 1 only): 0 = R rows in flight per team, 4 blocks/SM (<=128 regs);
@@ -173,17 +236,17 @@ cudaError_t launch_one(const GraphView& g, const BeamTask& t, int num_sms, cudaS
 // 3 = R/2 rows, 5 blocks/SM (<=96 regs).
 template <int TEAM, int CPL, int R, bool HALF>
 cudaError_t launch_w(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
-                     cudaStream_t stream, int* grid_out) {
+                     cudaStream_t stream, int* grid_out, const BuildBatch* fuse) {
     constexpr int RH = R >= 2 ? R / 2 : 1;
     switch (W) {
         case 1:
-            if (variant == 1) return launch_one<TEAM, CPL, 1, RH, 4, 6, HALF>(g, t, num_sms, stream, grid_out);
-            if (variant == 2) return launch_one<TEAM, CPL, 1, RH, 4, 8, HALF>(g, t, num_sms, stream, grid_out);
-            if (variant == 3) return launch_one<TEAM, CPL, 1, RH, 4, 5, HALF>(g, t, num_sms, stream, grid_out);
-            return launch_one<TEAM, CPL, 1, R, 4, 4, HALF>(g, t, num_sms, stream, grid_out);
-        case 2: return launch_one<TEAM, CPL, 2, R, 2, 1, HALF>(g, t, num_sms, stream, grid_out);
-        case 4: return launch_one<TEAM, CPL, 4, R, 1, 1, HALF>(g, t, num_sms, stream, grid_out);
-        case 8: return launch_one<TEAM, CPL, 8, R, 1, 1, HALF>(g, t, num_sms, stream, grid_out);
+            if (variant == 1) return launch_one<TEAM, CPL, 1, RH, 4, 6, HALF>(g, t, num_sms, stream, grid_out, fuse);
+            if (variant == 2) return launch_one<TEAM, CPL, 1, RH, 4, 8, HALF>(g, t, num_sms, stream, grid_out, fuse);
+            if (variant == 3) return launch_one<TEAM, CPL, 1, RH, 4, 5, HALF>(g, t, num_sms, stream, grid_out, fuse);
+            return launch_one<TEAM, CPL, 1, R, 4, 4, HALF>(g, t, num_sms, stream, grid_out, fuse);
+        case 2: return launch_one<TEAM, CPL, 2, R, 2, 1, HALF>(g, t, num_sms, stream, grid_out, fuse);
+        case 4: return launch_one<TEAM, CPL, 4, R, 1, 1, HALF>(g, t, num_sms, stream, grid_out, fuse);
+        case 8: return launch_one<TEAM, CPL, 8, R, 1, 1, HALF>(g, t, num_sms, stream, grid_out, fuse);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -191,15 +254,15 @@ cudaError_t launch_w(const GraphView& g, const BeamTask& t, int W, int variant, 
 // (TEAM, CPL) by the number of 16-byte chunks per stored row (fp32: d/4, fp16: d/8).
 template <bool HALF>
 cudaError_t launch_by_chunks(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
-                             cudaStream_t stream, int* grid_out) {
+                             cudaStream_t stream, int* grid_out, const BuildBatch* fuse) {
     const int nc = g.nchunk;
-    if (nc <= 16) return launch_w<8, 2, 8, HALF>(g, t, W, variant, num_sms, stream, grid_out);  // 2 chunks/lane: 8 rows in flight
-    if (nc == 24) return launch_w<8, 3, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out);  // d=96 fp32: exact fit
-    if (nc <= 32) return launch_w<8, 4, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out);
-    if (nc <= 64) return launch_w<16, 4, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out);
-    if (nc <= 128) return launch_w<32, 4, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out);
-    if (nc <= 256) return launch_w<32, 8, 2, HALF>(g, t, W, variant, num_sms, stream, grid_out);
-    if (nc <= 512) return launch_w<32, 16, 1, HALF>(g, t, W, variant, num_sms, stream, grid_out);
+    if (nc <= 16) return launch_w<8, 2, 8, HALF>(g, t, W, variant, num_sms, stream, grid_out, fuse);  // 2 chunks/lane: 8 rows in flight
+    if (nc == 24) return launch_w<8, 3, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out, fuse);  // d=96 fp32: exact fit
+    if (nc <= 32) return launch_w<8, 4, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out, fuse);
+    if (nc <= 64) return launch_w<16, 4, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out, fuse);
+    if (nc <= 128) return launch_w<32, 4, 4, HALF>(g, t, W, variant, num_sms, stream, grid_out, fuse);
+    if (nc <= 256) return launch_w<32, 8, 2, HALF>(g, t, W, variant, num_sms, stream, grid_out, fuse);
+    if (nc <= 512) return launch_w<32, 16, 1, HALF>(g, t, W, variant, num_sms, stream, grid_out, fuse);
     return cudaErrorInvalidValue;
 }
 

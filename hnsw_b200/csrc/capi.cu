@@ -790,7 +790,6 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
             int W = 1;
             if (!h->pick_warps(efc, hb, 0, h->bp.warps_per_query, n_items, W))
                 return fail("efConstruction/hash_bits need more shared memory than one SM has");
-            BH_CUDA(bh::launch_beam(g, t, W, h->beam_variant(efc, hb), h->num_sms, h->stream, nullptr));
             bh::BuildBatch b{};
             b.items = t.items;
             b.cand_lists = h->cand_lists.p;
@@ -812,9 +811,12 @@ int add_impl(bh_index* h, int64_t n, const float* x, const int32_t* preset_level
             b.max_special = std::min(16, std::max(2, (16 * 1024) / (4 * h->row_floats())));  // (wide rows: a larger
             // staging budget than 16 KB per warp was measured slower at 768-d and 960-d)
             b.build_counters = h->build_counters.p;
-            BH_CUDA(bh::launch_select_and_link(g, b, h->num_sms, h->stream));
+            // rows above 512 B: selection + forward links run in the traversal kernel's epilogue (see launch_one)
+            const bool fuse = h->row_floats() / 4 > 32;
+            BH_CUDA(bh::launch_beam(g, t, W, h->beam_variant(efc, hb), h->num_sms, h->stream, nullptr, fuse ? &b : nullptr));
+            if (!fuse) BH_CUDA(bh::launch_select_and_link(g, b, h->num_sms, h->stream));
             BH_CUDA(bh::launch_backlinks(g, b, h->num_sms, h->stream));
-            bh::count_launch(3);
+            bh::count_launch(fuse ? 2 : 3);
         }
         if (r.new_entry >= 0) {  // add_with_locks tail: a taller point becomes the entry point
             h->entry_point = r.new_entry;

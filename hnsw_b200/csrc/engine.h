@@ -41,8 +41,6 @@ struct BeamTask {
 };
 
 size_t beam_group_smem(int d, int ef, int hash_bits, int deg, int rk = 0);
-cudaError_t launch_beam(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
-                        cudaStream_t stream, int* grid_out);
 
 // ---- construction kernels (build_kernels.cu) ------------------------------------
 struct BuildBatch {
@@ -68,6 +66,10 @@ struct BuildBatch {
     unsigned long long* build_counters;  // device [6] or null (see BeamTask)
 };
 
+// `fuse` (construction only): run the selection + forward links + back-edge staging of each item in the
+// traversal kernel's epilogue instead of a separate launch_select_and_link
+cudaError_t launch_beam(const GraphView& g, const BeamTask& t, int W, int variant, int num_sms,
+                        cudaStream_t stream, int* grid_out, const BuildBatch* fuse = nullptr);
 cudaError_t launch_select_and_link(const GraphView& g, const BuildBatch& b, int num_sms, cudaStream_t stream);
 cudaError_t launch_backlinks(const GraphView& g, const BuildBatch& b, int num_sms, cudaStream_t stream);
 

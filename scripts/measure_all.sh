@@ -1,3 +1,6 @@
+# Round-end measurement batch on ONE B200 (run under gpurun): GPU tests, smoke, bench lines for every config, the CPU arm,
+# ncu captures of the traversal kernel (summaries + traffic json written next to the logs in gpurun_out/) and the launch list.
+# Every ncu run follows a plain run of the identical command (B200_PROFILING.md).
 set -x
 python -m pytest tests -m gpu -q > gpurun_out/r2_pytest_final.log 2>&1; tail -3 gpurun_out/r2_pytest_final.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; tail -1 gpurun_out/r2_smoke.log
