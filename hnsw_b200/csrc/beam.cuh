@@ -201,6 +201,18 @@ struct Beam {
         }
     }
 
+    // L2 prefetch of the 128-byte lines of cand_id[0..n)'s rows, spread over the group's lanes.
+    __device__ __forceinline__ void prefetch_rows(int n) const {
+        const int lines = (g.nchunk + 7) >> 3;  // 128-byte lines per row
+        const char* base = reinterpret_cast<const char*>(g.vecs);
+        const size_t row_bytes = (size_t)g.nchunk * 16;
+        for (int i = wig * 32 + lane; i < n * lines; i += 32 * W) {
+            const int r = i / lines, l = i - r * lines;
+            const char* p = base + (size_t)s.cand_id[r] * row_bytes + (size_t)l * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        }
+    }
+
     __device__ __forceinline__ const int32_t* row_ptr(int v, int level, int& deg) const {
         if (level == 0) {
             deg = g.deg0;
@@ -386,8 +398,14 @@ struct Beam {
     // On return ctrl[1] = list size.
     // sel/rk: faiss IDSelectorBitmap and the k of the selector-filtered result list (nullptr/0: none).
     //          The selector decides only what enters the RESULT list; traversal is unchanged.
+    // work_counter / n_items (may be null): the launch's work counter. Once it has run past n_items the launch
+    // is DRAINING — resident queries finish one by one and HBM is no longer saturated — and a hop's candidate
+    // rows are first prefetched into L2 all at once, so that the register gathers that follow (R rows per team
+    // and round, several dependent rounds per hop) wait on L2 instead of DRAM. (In steady state the same
+    // prefetch is neutral: the memory system is saturated either way.)
     __device__ void run(int level, int ef, int ef_stop, int max_steps, int vmode, int hash_bits, uint32_t start_id,
-                        float start_d, BeamStats& st, const uint8_t* sel = nullptr, int rk = 0) const {
+                        float start_d, BeamStats& st, const uint8_t* sel = nullptr, int rk = 0,
+                        const int* work_counter = nullptr, int n_items = 0) const {
         int lsize = 0, cursor = 0, hcount = 0, nstep = 0, rsize = 0, rcursor = 0;
         const int hlimit = (3 << hash_bits) >> 2;  // kVisitedExact: reset above 75 % load
         if (wig == 0) {
@@ -474,6 +492,7 @@ struct Beam {
             const int n_new = s.ctrl[0];
             if (n_new < 0) break;
             BH_T(t4);
+            if (work_counter && n_new > NT * R && __ldcg(work_counter) >= n_items) prefetch_rows(n_new);
             compute_dists(n_new);
             group_sync();
             BH_T(t5);

@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(32 * W * G, MINB) beam_kernel(GraphView g, Bea
         uint32_t cur_id = 0;
         float cur_d = 0.f;
         beam.descend(stop_level, cur_id, cur_d, st);
-        beam.run(level, t.ef, t.ef_stop, t.max_steps, t.visited_mode, t.hash_bits, cur_id, cur_d, st, t.sel, rk);
+        beam.run(level, t.ef, t.ef_stop, t.max_steps, t.visited_mode, t.hash_bits, cur_id, cur_d, st, t.sel, rk,
+                 t.drain_prefetch ? t.counter : nullptr, t.n_items);
 
         if (wig == 0) {
             const int lsize = t.sel ? s.ctrl[2] : s.ctrl[1];

@@ -32,6 +32,7 @@ struct BeamTask {
     unsigned long long* build_counters;  // device [6] or null: {ndis0, nhops0, ndis_up, nhops_up, sel_rows, bl_rows}
     const uint8_t* sel;  // device IDSelectorBitmap over the shard's ids, or null (search mode only)
     int* counter;    // device work counter, zeroed before launch
+    int drain_prefetch;  // 1: L2-prefetch a hop's rows once the launch is draining (beam.cuh run())
     int pdl;         // 1: launched with programmatic stream serialisation (search mode; see capi.cu search_device)
     // sharded search (search mode only): instead of D / I the epilogue publishes each query's k results as
     // packed (order-preserving distance bits << 32 | local id) keys, ~0 = empty, straight into the gather
