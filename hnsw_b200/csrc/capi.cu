@@ -502,7 +502,7 @@ int next_ring_counter(SearchCtx& c, cudaStream_t st, int** counter) {
 int search_device_impl(const bh_index* h, cudaStream_t stream, int* counter, int64_t n, const float* xq_d,
                        int64_t k, float* D_d, int64_t* I_d, int32_t* stats_d, const bh_search_params* params,
                        const uint8_t* sel_dev = nullptr, int n_shard_out = 0,
-                       unsigned long long* const* shard_out = nullptr, bool overlap = false) {
+                       unsigned long long* const* shard_out = nullptr, bool overlap = false, bool solo = true) {
     const int efS = (params && params->efSearch > 0) ? params->efSearch : h->efSearch;
     bool crd = h->check_relative_distance;
     if (params && params->check_relative_distance == 1) crd = true;
@@ -533,7 +533,10 @@ int search_device_impl(const bh_index* h, cudaStream_t stream, int* counter, int
     t.n_shard_out = n_shard_out;
     for (int p = 0; p < n_shard_out; p++) t.shard_out[p] = shard_out[p];
     t.pdl = overlap ? 1 : 0;
-    t.drain_prefetch = 1;  // search: -2..4 % per isolated launch (10k..1k queries); construction rounds: +2 % slower, off there
+    // drain-mode prefetch (beam.cuh run()): -1.5..4 % for a launch that drains on an otherwise idle GPU (one
+    // synchronous call; 10k..1k queries), but +3 % when the next launch is already filling the freed slots
+    // (overlapping launches, the chunks of a pageable batch) and +2 % in construction rounds — off there
+    t.drain_prefetch = (overlap || !solo) ? 0 : 1;
     if (!overlap) BH_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));  // (overlap: the caller hands out a zeroed counter)
     BH_CUDA(bh::launch_beam(h->view(), t, W, h->beam_variant(ef + rk, hb), h->num_sms, stream, nullptr));
     bh::count_launch();
@@ -1099,7 +1102,8 @@ int bh_index_search(const bh_index* h, int64_t n, const float* x, int64_t k, flo
         if (stats_host) BH_CUDA(l.hS.reserve((size_t)chunk * 4));
         copy_rows_padded(l.hq.p, x + (size_t)i0 * d, m, d, dp);
         if (int rc = search_device_impl(h, l.stream, c.counters.p + li, m, l.hq.dev, k, l.hD.dev, l.hI.dev,
-                                        stats_host ? l.hS.dev : nullptr, params, sel_dev))
+                                        stats_host ? l.hS.dev : nullptr, params, sel_dev, 0, nullptr, false,
+                                        /*solo=*/chunk >= n))
             return rc;
         BH_CUDA(cudaEventRecord(l.done, l.stream));
         l.pending_i0 = i0;
