@@ -115,7 +115,7 @@ def kernel_source_sha():
     """Identity of the traversal kernel's sources: profiles/*traffic*.json is only quoted when it was
     captured from this exact code."""
     h = hashlib.sha256()
-    for fn in ("beam.cuh", "beam_kernel_impl.cuh", "common.cuh", "engine.h"):
+    for fn in ("beam.cuh", "beam_kernel_impl.cuh", "beam_launch.cuh", "select.cuh", "common.cuh", "engine.h"):
         with open(os.path.join(ROOT, "hnsw_b200", "csrc", fn), "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:16]

@@ -35,7 +35,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     env["PATH"] = "/usr/bin:/bin:/usr/local/cuda/bin:" + env.get("PATH", "")
     for k in ("CXX", "CC"):
         env.pop(k, None)
-    cmd = ["make", "-C", _HERE, "-j4"] + (["-B"] if force else [])
+    cmd = ["make", "-C", _HERE, "-j8"] + (["-B"] if force else [])
     r = subprocess.run(cmd, env=env, capture_output=not verbose, text=True)
     if r.returncode != 0:
         raise RuntimeError("building libb200hnsw.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
