@@ -609,6 +609,9 @@ def run_b200(a):
             # the kernel actually touched (re-scored vertices included) are beside it
             "roofline": {"bound": "hbm", "achieved": round(achieved_exact, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved_exact / peak, 4), "traffic": traffic, "traffic_source": traffic_source,
+                         # DRAM-level view: measured DRAM bytes of a launch / step time (L2 serves the entry region, so
+                         # this is below the algorithmic figure; "frac" can read above 1.0, this cannot)
+                         "traffic_frac": None if traffic is None else round(traffic / (ms_step * 1e-3) / 1e9 / peak, 4),
                          "peak_source": peak_src, "kernel": "beam_kernel (one launch per step)",
                          "bytes_per_launch": round(sel["bytes_per_query_exact"] * a.nq),
                          "touched": {"achieved": round(achieved, 1), "frac": round(achieved / peak, 4),
