@@ -12,8 +12,10 @@
 // below cites the appendix paragraph it restates. It is pinned only by
 //   (1) std::mt19937 known answers (standard-defined),
 //   (2) brute-force exact kNN (recall), and
-//   (3) structural invariants of the built graph
-// — see tests/test_oracle.py.
+//   (3) structural invariants of the built graph, and
+//   (4) a 7-vertex graph worked by hand from the published algorithm (neighbour rows,
+//       visit order, results) that the oracle and the GPU must both reproduce
+// — see tests/test_oracle.py and tests/test_handworked_golden.py.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs may load this library. The product (hnsw_b200/) never does.
