@@ -1573,6 +1573,8 @@ int bh_shards_post(bh_shards* s, int64_t n, const float* x, int64_t k, const bh_
 // per rank) fills the other slices, then calls bh_shards_collect with wait_for_peers = 0
 int bh_shards_gather(bh_shards* s, int64_t n, int64_t k, void** ptr) {
     if (!s || !ptr) return fail("null argument");
+    if (n < 1 || n > s->max_q || k < 1 || k > s->max_k) return fail("shards_gather: n / k exceed max_queries / max_k");
+    std::lock_guard<std::mutex> lk(s->mu);
     *ptr = gather_slot(s->arena, s->parity_elems, (int)(s->epoch % kShardRing), 0, n, k);
     return 0;
 }
@@ -1627,7 +1629,9 @@ int bh_shards_join(bh_shards* s, void* stream) {
 // this rank's own lists of the current call as (D, I) with LOCAL ids (device buffers [n][k])
 int bh_shards_local_lists(bh_shards* s, int64_t n, int64_t k, float* distances, int64_t* labels) {
     if (!s || !distances || !labels) return fail("null argument");
+    if (n < 1 || n > s->max_q || k < 1 || k > s->max_k) return fail("shards_local_lists: n / k exceed max_queries / max_k");
     const bh_index* h = s->local;
+    std::lock_guard<std::mutex> lk(s->mu);
     BH_CUDA(cudaSetDevice(h->device));
     BH_CUDA(bh::launch_unpack(gather_slot(s->arena, s->parity_elems, (int)(s->epoch % kShardRing), s->rank, n, k), n * k,
                               h->metric == BH_METRIC_L2, distances, labels, h->stream));
