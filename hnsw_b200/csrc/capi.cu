@@ -1067,7 +1067,12 @@ int bh_index_search(const bh_index* h, int64_t n, const float* x, int64_t k, flo
     // next needed or at the end. Staging chunk i+1 overlaps the traversal of chunk i, and the chunks'
     // kernels fill each other's tails; there is no separate H2D / D2H phase.
     const int d = h->d, dp = h->dp;
-    int64_t chunk = (n + 3) / 4;                       // 4 chunks for a mid-size batch
+    // a mid-size batch: one chunk per lane while the staging copy is small beside the traversal (rows up to
+    // 512 B), four chunks for wider rows, where a smaller first chunk starts the GPU sooner (measured, 10k
+    // queries: 1M x 128 efSearch 64: 2.80 ms with 3 chunks, 2.88 with 4, 3.00 with 6-8, 2.91 with 1;
+    // 300k x 960 efSearch 48: 12.9 / 12.4 / 12.5 / 14.1 ms; profiles/README.md)
+    const int nchunks = (size_t)dp * sizeof(float) <= 512 ? kLanes : 4;
+    int64_t chunk = (n + nchunks - 1) / nchunks;
     chunk = std::max<int64_t>(chunk, 2048);            // small batches: one launch
     chunk = std::min<int64_t>(chunk, 32768);           // bounds the staging memory
     chunk = std::min<int64_t>(chunk, n);
